@@ -1,0 +1,847 @@
+// lbm_gpu.cu -- host side of liblbm_b200.so: the C-ABI declared in include/lbm_gpu.h.
+//
+// Replaces the step loop of the reference's main() (d2q9-bgk.c:180-201) and the device
+// side of initialise()/finalise() (d2q9-bgk.c:2787-2857, :2871-2890).  No PyTorch, no
+// CPU fallback: every entry point either runs the CUDA path or returns an error.
+#include "lbm_gpu.h"
+#include "lbm_kernels.cuh"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return 1;
+}
+
+struct CudaError {
+  std::string what;
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char b_[512];                                                                           \
+      snprintf(b_, sizeof b_, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e_),        \
+               cudaGetErrorString(e_), __FILE__, __LINE__, #call);                            \
+      throw CudaError{b_};                                                                    \
+    }                                                                                         \
+  } while (0)
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+constexpr size_t kStagingBytes = 64u << 20;   // device staging for AoS<->SoA / mask / fields
+
+// descriptor exchanged between processes (lbm_gpu_ipc_export / _connect)
+struct IpcDesc {
+  uint32_t magic;
+  int32_t elem_size;
+  int32_t device;
+  int32_t pid;
+  int32_t nx, pitch, rows;
+  int32_t pad_;
+  long long row0;
+  long long plane_stride;
+  unsigned long long base_addr;       // only meaningful inside the exporting process
+  unsigned long long off_lattice[2];  // byte offsets inside the allocation
+  unsigned long long off_sync;
+  unsigned long long steps_done;
+  cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large");
+constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
+
+enum SyncWord { kFlagFromBelow = 0, kFlagFromAbove = 1, kBoundaryDone = 2, kScratch0 = 3, kScratch1 = 4,
+                kScratch2 = 5, kSyncWords = 8 };
+
+struct GridBase {
+  virtual ~GridBase() {}
+  virtual bool is_f64() const = 0;
+};
+
+template <typename real>
+struct Slab {
+  int device = 0;
+  long long row0 = 0;   // first global row
+  int rows = 0;         // local rows
+  int accel_row = -1;   // local row (1-based) of global row ny-2, or -1
+  char* base = nullptr; // the one allocation: lattice[2] | side[2] | mask | sync words
+  size_t bytes = 0;
+  size_t off_lattice[2] = {0, 0}, off_side[2] = {0, 0}, off_mask = 0, off_sync = 0;
+  real* lattice[2] = {nullptr, nullptr};
+  real* side[2] = {nullptr, nullptr};
+  uint32_t* mask = nullptr;
+  unsigned long long* sync = nullptr;
+  unsigned long long *av_lo = nullptr, *av_hi = nullptr;
+  size_t av_cap = 0;
+  void* staging = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long free_cells = 0;
+  // neighbour views
+  real* up_lattice[2] = {nullptr, nullptr};   // neighbour above (holds global row row0+rows)
+  real* dn_lattice[2] = {nullptr, nullptr};   // neighbour below (holds global row row0-1)
+  long long up_plane_stride = 0, dn_plane_stride = 0;
+  int dn_rows = 0;
+  unsigned long long* up_flag = nullptr;      // neighbour above's kFlagFromBelow
+  unsigned long long* dn_flag = nullptr;      // neighbour below's kFlagFromAbove
+  void* ipc_mapped[2] = {nullptr, nullptr};   // pointers to close on destroy
+};
+
+template <typename real> struct ParamT;
+template <> struct ParamT<float> { typedef lbm_param type; };
+template <> struct ParamT<double> { typedef lbm_param_f64 type; };
+
+template <typename real>
+class Grid : public GridBase {
+ public:
+  typedef typename ParamT<real>::type Param;
+  Param prm;
+  unsigned flags = 0;
+  int kernel = 0;
+  int pitch = 0, mask_pitch = 0;
+  bool slab_mode = false;      // one process per GPU: neighbours are other processes
+  bool connected = false;      // neighbour views are set
+  bool multi = false;          // more than one slab in the whole grid -> flag protocol
+  long long global_free_cells = -1;
+  long long steps_done = 0;
+  long long launches = 0;
+  double last_run_ms = 0.0, last_step_ms = 0.0;
+  std::vector<Slab<real>> slabs;
+
+  bool is_f64() const override { return sizeof(real) == 8; }
+
+  ~Grid() override {
+    for (auto& s : slabs) {
+      cudaSetDevice(s.device);
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      for (int i = 0; i < 2; i++)
+        if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
+      if (s.ev0) cudaEventDestroy(s.ev0);
+      if (s.ev1) cudaEventDestroy(s.ev1);
+      if (s.stream) cudaStreamDestroy(s.stream);
+      if (s.av_lo) cudaFree(s.av_lo);
+      if (s.staging) cudaFree(s.staging);
+      if (s.base) cudaFree(s.base);
+    }
+  }
+
+  // ---------------------------------------------------------------- allocation ----
+  void alloc_slab(Slab<real>& s) {
+    CK(cudaSetDevice(s.device));
+    const long long plane = (long long)(s.rows + 2) * pitch;
+    const size_t lat = (size_t)9 * plane * sizeof(real);
+    const size_t side = (size_t)6 * pitch * sizeof(real);
+    const size_t maskb = (size_t)s.rows * mask_pitch * sizeof(uint32_t);
+    size_t off = 0;
+    for (int i = 0; i < 2; i++) { s.off_lattice[i] = off; off = round_up(off + lat, 256); }
+    for (int i = 0; i < 2; i++) { s.off_side[i] = off; off = round_up(off + side, 256); }
+    s.off_mask = off; off = round_up(off + maskb, 256);
+    s.off_sync = off; off = round_up(off + kSyncWords * sizeof(unsigned long long), 256);
+    s.bytes = off;
+    CK(cudaMalloc((void**)&s.base, s.bytes));
+    for (int i = 0; i < 2; i++) {
+      s.lattice[i] = (real*)(s.base + s.off_lattice[i]);
+      s.side[i] = (real*)(s.base + s.off_side[i]);
+    }
+    s.mask = (uint32_t*)(s.base + s.off_mask);
+    s.sync = (unsigned long long*)(s.base + s.off_sync);
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&s.ev0));
+    CK(cudaEventCreate(&s.ev1));
+    CK(cudaMemsetAsync(s.base + s.off_side[0], 0, s.bytes - s.off_side[0], s.stream));
+    CK(cudaMalloc(&s.staging, kStagingBytes));
+  }
+
+  long long plane_stride(const Slab<real>& s) const { return (long long)(s.rows + 2) * pitch; }
+
+  void setup_geometry(int nx) {
+    pitch = (int)round_up(nx, 32);
+    mask_pitch = pitch / 32;
+    if (flags & LBM_GPU_KERNEL_SCALAR) kernel = LBM_GPU_KERNEL_SCALAR;
+    else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
+    else kernel = (nx % 4 == 0) ? LBM_GPU_KERNEL_VEC4 : LBM_GPU_KERNEL_SCALAR;
+    if (kernel != LBM_GPU_KERNEL_SCALAR && nx % 4 != 0)
+      throw CudaError{"the vector kernels need nx % 4 == 0"};
+  }
+
+  // ------------------------------------------------------------- lattice input ----
+  // cells: AoS rows for this slab (or NULL -> rest state); obstacles: rows for this slab
+  void load_slab(Slab<real>& s, const real* cells_aos, const void* obstacles, int cur) {
+    CK(cudaSetDevice(s.device));
+    const int nx = prm.nx;
+    if (cells_aos) {
+      upload_cells(s, cells_aos, cur);
+    } else {
+      const real w0 = prm.density * (real)4 / (real)9;     // d2q9-bgk.c:2802-2804
+      const real w1 = prm.density / (real)9;
+      const real w2 = prm.density / (real)36;
+      const long long total = plane_stride(s);
+      lbm::lbm_init_rest<real><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
+          s.lattice[cur], plane_stride(s), pitch, nx, s.rows, w0, w1, w2);
+      CK(cudaGetLastError());
+      launches++;
+    }
+    // mask
+    unsigned long long* counter = s.sync + kScratch0;
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s.stream));
+    if (obstacles) {
+      const bool bits = (flags & LBM_GPU_OBST_BITS) != 0;
+      const int wpr = (nx + 31) / 32;
+      const size_t row_bytes = bits ? (size_t)wpr * 4 : (size_t)nx * 4;
+      const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / row_bytes);
+      for (int r = 0; r < s.rows; r += chunk_rows) {
+        const int n = std::min(chunk_rows, s.rows - r);
+        CK(cudaMemcpyAsync(s.staging, (const char*)obstacles + (size_t)r * row_bytes, (size_t)n * row_bytes,
+                           cudaMemcpyHostToDevice, s.stream));
+        if (bits) {
+          const long long words = (long long)n * wpr;
+          lbm::lbm_copy_mask_bits<<<(unsigned)((words + 255) / 256), 256, 0, s.stream>>>(
+              (const uint32_t*)s.staging, s.mask, mask_pitch, nx, r, n, counter);
+        } else {
+          const long long threads = (long long)n * wpr * 32;
+          lbm::lbm_pack_mask<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
+              (const int*)s.staging, s.mask, mask_pitch, nx, r, n, counter);
+        }
+        CK(cudaGetLastError());
+        launches++;
+        CK(cudaStreamSynchronize(s.stream));   // staging is reused by the next chunk
+      }
+    }
+    unsigned long long blocked = 0;
+    CK(cudaMemcpyAsync(&blocked, counter, sizeof blocked, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    s.free_cells = (long long)s.rows * nx - (long long)blocked;
+  }
+
+  void upload_cells(Slab<real>& s, const real* cells_aos, int cur) {
+    CK(cudaSetDevice(s.device));
+    const int nx = prm.nx;
+    const size_t row_bytes = (size_t)nx * 9 * sizeof(real);
+    const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / row_bytes);
+    if (row_bytes > kStagingBytes) throw CudaError{"nx too large for the AoS staging buffer"};
+    for (int r = 0; r < s.rows; r += chunk_rows) {
+      const int n = std::min(chunk_rows, s.rows - r);
+      const long long ncells = (long long)n * nx;
+      CK(cudaMemcpyAsync(s.staging, (const char*)cells_aos + (size_t)r * row_bytes, (size_t)n * row_bytes,
+                         cudaMemcpyHostToDevice, s.stream));
+      lbm::lbm_aos_to_soa<real><<<(unsigned)((ncells * 9 + 255) / 256), 256, 0, s.stream>>>(
+          (const real*)s.staging, s.lattice[cur], plane_stride(s), pitch, nx, r + 1, ncells);
+      CK(cudaGetLastError());
+      launches++;
+      CK(cudaStreamSynchronize(s.stream));
+    }
+  }
+
+  // ------------------------------------------------------------------ wiring ----
+  // all slabs live in this process: neighbours are reached through peer access
+  void connect_local() {
+    const int n = (int)slabs.size();
+    for (int i = 0; i < n; i++) {
+      Slab<real>& s = slabs[i];
+      Slab<real>& up = slabs[(i + 1) % n];
+      Slab<real>& dn = slabs[(i + n - 1) % n];
+      CK(cudaSetDevice(s.device));
+      for (Slab<real>* o : {&up, &dn}) {
+        if (o->device != s.device) {
+          int can = 0;
+          CK(cudaDeviceCanAccessPeer(&can, s.device, o->device));
+          if (!can) throw CudaError{"peer access between the selected GPUs is not available"};
+          cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+          cudaGetLastError();
+        }
+      }
+      for (int b = 0; b < 2; b++) { s.up_lattice[b] = up.lattice[b]; s.dn_lattice[b] = dn.lattice[b]; }
+      s.up_plane_stride = plane_stride(up);
+      s.dn_plane_stride = plane_stride(dn);
+      s.dn_rows = dn.rows;
+      s.up_flag = up.sync + kFlagFromBelow;
+      s.dn_flag = dn.sync + kFlagFromAbove;
+    }
+    multi = n > 1;
+    connected = true;
+  }
+
+  void prepare() {
+    if (!connected) throw CudaError{"lattice is not connected to its neighbours yet"};
+    const int cur = (int)(steps_done & 1);
+    for (auto& s : slabs) {
+      CK(cudaSetDevice(s.device));
+      lbm::PrepareArgs<real> a;
+      a.cur = s.lattice[cur];
+      a.side_cur = s.side[cur];
+      a.mask = s.mask;
+      a.up_ghost = s.up_lattice[cur];
+      a.dn_ghost = s.dn_lattice[cur] + (long long)(s.dn_rows + 1) * pitch;
+      a.up_plane_stride = s.up_plane_stride;
+      a.dn_plane_stride = s.dn_plane_stride;
+      a.plane_stride = plane_stride(s);
+      a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch; a.accel_row = s.accel_row;
+      a.aw1 = prm.density * prm.accel / (real)9;      // d2q9-bgk.c:230-231
+      a.aw2 = prm.density * prm.accel / (real)36;
+      lbm::lbm_prepare<real><<<(prm.nx + 127) / 128, 128, 0, s.stream>>>(a);
+      CK(cudaGetLastError());
+      launches++;
+    }
+    for (auto& s : slabs) { CK(cudaSetDevice(s.device)); CK(cudaStreamSynchronize(s.stream)); }
+  }
+
+  // -------------------------------------------------------------------- run ----
+  template <bool STRICT, bool MULTI>
+  void launch_step(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block) {
+    if (kernel == LBM_GPU_KERNEL_SCALAR)
+      lbm::lbm_step_scalar<real, STRICT, MULTI><<<grid, block, 0, s.stream>>>(a);
+    else
+      lbm::lbm_step_vec4<real, STRICT, MULTI><<<grid, block, 0, s.stream>>>(a);
+  }
+
+  void run(int n_steps, double* sums_out) {
+    if (!connected) throw CudaError{"lattice is not connected to its neighbours yet"};
+    if (n_steps <= 0) return;
+    const bool strict = (flags & LBM_GPU_STRICT) != 0;
+    for (auto& s : slabs) {
+      CK(cudaSetDevice(s.device));
+      if (s.av_cap < (size_t)n_steps) {
+        if (s.av_lo) CK(cudaFree(s.av_lo));
+        s.av_lo = nullptr;
+        s.av_cap = std::max<size_t>((size_t)n_steps, 1024);
+        CK(cudaMalloc((void**)&s.av_lo, 2 * s.av_cap * sizeof(unsigned long long)));
+        s.av_hi = s.av_lo + s.av_cap;
+      }
+      CK(cudaMemsetAsync(s.av_lo, 0, 2 * s.av_cap * sizeof(unsigned long long), s.stream));
+    }
+    for (auto& s : slabs) { CK(cudaSetDevice(s.device)); CK(cudaEventRecord(s.ev0, s.stream)); }
+
+    const int vec = (kernel == LBM_GPU_KERNEL_SCALAR) ? 1 : 4;
+    const int nxv = prm.nx / vec;
+    const int bx = (int)std::min<long long>(256, round_up(nxv, 32));
+    const int by = 256 / bx;
+    const dim3 block(bx, by);
+    for (int t = 0; t < n_steps; t++) {
+      const unsigned long long step = (unsigned long long)(steps_done + t);
+      const int src = (int)(step & 1), dst = src ^ 1;
+      for (auto& s : slabs) {
+        CK(cudaSetDevice(s.device));
+        lbm::StepArgs<real> a;
+        a.src = s.lattice[src];
+        a.dst = s.lattice[dst];
+        a.side_src = s.side[src];
+        a.side_dst = s.side[dst];
+        a.mask = s.mask;
+        a.av_lo = s.av_lo + t;
+        a.av_hi = s.av_hi + t;
+        a.up_ghost = s.up_lattice[dst];
+        a.dn_ghost = s.dn_lattice[dst] + (long long)(s.dn_rows + 1) * pitch;
+        a.up_plane_stride = s.up_plane_stride;
+        a.dn_plane_stride = s.dn_plane_stride;
+        a.flag_from_below = s.sync + kFlagFromBelow;
+        a.flag_from_above = s.sync + kFlagFromAbove;
+        a.up_flag = s.up_flag;
+        a.dn_flag = s.dn_flag;
+        a.boundary_done = s.sync + kBoundaryDone;
+        a.step = step;
+        a.plane_stride = plane_stride(s);
+        a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch;
+        a.accel_row = s.accel_row;
+        a.tiles_x = (nxv + bx - 1) / bx;
+        a.tiles_y = (s.rows + by - 1) / by;
+        a.omega = prm.omega;
+        a.aw1 = prm.density * prm.accel / (real)9;
+        a.aw2 = prm.density * prm.accel / (real)36;
+        const dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y));
+        if (strict) { if (multi) launch_step<true, true>(s, a, grid, block); else launch_step<true, false>(s, a, grid, block); }
+        else        { if (multi) launch_step<false, true>(s, a, grid, block); else launch_step<false, false>(s, a, grid, block); }
+        CK(cudaGetLastError());
+        launches++;
+      }
+    }
+    double ms_max = 0.0;
+    for (auto& s : slabs) { CK(cudaSetDevice(s.device)); CK(cudaEventRecord(s.ev1, s.stream)); }
+    for (auto& s : slabs) {
+      CK(cudaSetDevice(s.device));
+      CK(cudaStreamSynchronize(s.stream));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+      ms_max = std::max(ms_max, (double)ms);
+    }
+    last_run_ms = ms_max;
+    last_step_ms = ms_max / n_steps;
+    steps_done += n_steps;
+
+    if (sums_out) {
+      std::vector<unsigned long long> lo(n_steps), hi(n_steps);
+      std::vector<unsigned __int128> tot(n_steps, 0);
+      for (auto& s : slabs) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaMemcpy(lo.data(), s.av_lo, n_steps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hi.data(), s.av_hi, n_steps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int t = 0; t < n_steps; t++) tot[t] += ((unsigned __int128)hi[t] << 64) | lo[t];
+      }
+      for (int t = 0; t < n_steps; t++) sums_out[t] = (double)((long double)tot[t] / (long double)LBM_FIX_SCALE);
+    }
+  }
+
+  long long local_free_cells() const {
+    long long n = 0;
+    for (auto& s : slabs) n += s.free_cells;
+    return n;
+  }
+  long long divisor() const { return global_free_cells >= 0 ? global_free_cells : local_free_cells(); }
+
+  // ---------------------------------------------------------------- outputs ----
+  Slab<real>& slab_of_row(long long grow) {
+    for (auto& s : slabs)
+      if (grow >= s.row0 && grow < s.row0 + s.rows) return s;
+    throw CudaError{"row is not held by this process"};
+  }
+
+  void download_rows(long long row0, long long nrows, real* out) {
+    const int cur = (int)(steps_done & 1);
+    const int nx = prm.nx;
+    const size_t row_bytes = (size_t)nx * 9 * sizeof(real);
+    if (row_bytes > kStagingBytes) throw CudaError{"nx too large for the AoS staging buffer"};
+    const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / row_bytes);
+    long long g = row0;
+    while (g < row0 + nrows) {
+      Slab<real>& s = slab_of_row(g);
+      CK(cudaSetDevice(s.device));
+      const int n = (int)std::min<long long>({(long long)chunk_rows, s.row0 + s.rows - g, row0 + nrows - g});
+      const long long ncells = (long long)n * nx;
+      lbm::lbm_soa_to_aos<real><<<(unsigned)((ncells * 9 + 255) / 256), 256, 0, s.stream>>>(
+          s.lattice[cur], (real*)s.staging, plane_stride(s), pitch, nx, (int)(g - s.row0) + 1, ncells);
+      CK(cudaGetLastError());
+      launches++;
+      CK(cudaMemcpyAsync((char*)out + (size_t)(g - row0) * row_bytes, s.staging, (size_t)n * row_bytes,
+                         cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+      g += n;
+    }
+  }
+
+  void final_fields(long long row0, long long nrows, real* ux, real* uy, real* u, real* p) {
+    const int cur = (int)(steps_done & 1);
+    const int nx = prm.nx;
+    const size_t row_bytes = (size_t)nx * sizeof(real);
+    const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / (4 * row_bytes));
+    long long g = row0;
+    while (g < row0 + nrows) {
+      Slab<real>& s = slab_of_row(g);
+      CK(cudaSetDevice(s.device));
+      const int n = (int)std::min<long long>({(long long)chunk_rows, s.row0 + s.rows - g, row0 + nrows - g});
+      const long long ncells = (long long)n * nx;
+      real* st = (real*)s.staging;
+      real* d_ux = ux ? st : nullptr;
+      real* d_uy = uy ? st + ncells : nullptr;
+      real* d_u = u ? st + 2 * ncells : nullptr;
+      real* d_p = p ? st + 3 * ncells : nullptr;
+      lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
+          s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, nx, (int)(g - s.row0) + 1, n,
+          prm.density, d_ux, d_uy, d_u, d_p, nullptr, nullptr);
+      CK(cudaGetLastError());
+      launches++;
+      const size_t off = (size_t)(g - row0) * nx;
+      if (ux) CK(cudaMemcpyAsync(ux + off, d_ux, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
+      if (uy) CK(cudaMemcpyAsync(uy + off, d_uy, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
+      if (u) CK(cudaMemcpyAsync(u + off, d_u, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
+      if (p) CK(cudaMemcpyAsync(p + off, d_p, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+      g += n;
+    }
+  }
+
+  double av_velocity_sum() {
+    const int cur = (int)(steps_done & 1);
+    unsigned __int128 tot = 0;
+    for (auto& s : slabs) {
+      CK(cudaSetDevice(s.device));
+      unsigned long long* lo = s.sync + kScratch1;
+      unsigned long long* hi = s.sync + kScratch2;
+      CK(cudaMemsetAsync(lo, 0, 2 * sizeof(unsigned long long), s.stream));
+      const long long ncells = (long long)s.rows * prm.nx;
+      lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
+          s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, prm.nx, 1, s.rows, prm.density,
+          nullptr, nullptr, nullptr, nullptr, lo, hi);
+      CK(cudaGetLastError());
+      launches++;
+      unsigned long long w[2];
+      CK(cudaMemcpyAsync(w, lo, sizeof w, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+      tot += ((unsigned __int128)w[1] << 64) | w[0];
+    }
+    return (double)((long double)tot / (long double)LBM_FIX_SCALE);
+  }
+};
+
+// split ny rows over n slabs: remainder spread over the first slabs
+void split_rows(long long ny, int n, std::vector<long long>& row0, std::vector<int>& rows) {
+  row0.resize(n);
+  rows.resize(n);
+  const long long base = ny / n, rem = ny % n;
+  long long r = 0;
+  for (int i = 0; i < n; i++) {
+    rows[i] = (int)(base + (i < rem ? 1 : 0));
+    row0[i] = r;
+    r += rows[i];
+  }
+}
+
+template <typename real>
+int create_impl(const typename ParamT<real>::type* params, const real* cells_aos, const void* obstacles,
+                int n_gpus, const int* device_ids, unsigned flags, lbm_gpu** out) {
+  if (!params || !out) return fail("lbm_gpu_create: NULL argument");
+  *out = nullptr;
+  if (params->nx < 1 || params->ny < 2) return fail("lbm_gpu_create: need nx >= 1 and ny >= 2 (got %d x %d)", params->nx, params->ny);
+  if (n_gpus < 1) return fail("lbm_gpu_create: n_gpus must be >= 1");
+  if (params->ny < n_gpus) return fail("lbm_gpu_create: fewer rows (%d) than GPUs (%d)", params->ny, n_gpus);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail("lbm_gpu_create: no CUDA device available (this library has no CPU fallback)");
+  }
+  std::unique_ptr<Grid<real>> g(new Grid<real>());
+  try {
+    g->prm = *params;
+    g->flags = flags;
+    g->setup_geometry(params->nx);
+    std::vector<long long> row0;
+    std::vector<int> rows;
+    split_rows(params->ny, n_gpus, row0, rows);
+    g->slabs.resize(n_gpus);
+    const size_t cell_row = (size_t)params->nx * 9;
+    const size_t obst_row_bytes = (flags & LBM_GPU_OBST_BITS) ? (size_t)((params->nx + 31) / 32) * 4 : (size_t)params->nx * 4;
+    for (int i = 0; i < n_gpus; i++) {
+      Slab<real>& s = g->slabs[i];
+      s.device = device_ids ? device_ids[i] : i;
+      if (s.device < 0 || s.device >= ndev) return fail("lbm_gpu_create: device %d not available (%d visible)", s.device, ndev);
+      s.row0 = row0[i];
+      s.rows = rows[i];
+      const long long ar = (long long)params->ny - 2;
+      s.accel_row = (ar >= s.row0 && ar < s.row0 + s.rows) ? (int)(ar - s.row0) + 1 : -1;
+      g->alloc_slab(s);
+      g->load_slab(s, cells_aos ? cells_aos + (size_t)s.row0 * cell_row : nullptr,
+                   obstacles ? (const char*)obstacles + (size_t)s.row0 * obst_row_bytes : nullptr, 0);
+    }
+    g->connect_local();
+    g->prepare();
+  } catch (const CudaError& e) {
+    return fail("lbm_gpu_create: %s", e.what.c_str());
+  }
+  *out = reinterpret_cast<lbm_gpu*>(static_cast<GridBase*>(g.release()));
+  return 0;
+}
+
+template <typename real>
+Grid<real>* as_grid(lbm_gpu* h, const char* fn) {
+  if (!h) { fail("%s: NULL handle", fn); return nullptr; }
+  GridBase* b = reinterpret_cast<GridBase*>(h);
+  if (b->is_f64() != (sizeof(real) == 8)) {
+    fail("%s: handle was created for %s", fn, b->is_f64() ? "double precision (use the _f64 entry points)" : "single precision");
+    return nullptr;
+  }
+  return static_cast<Grid<real>*>(b);
+}
+
+template <typename real, typename F>
+int guarded(lbm_gpu* h, const char* fn, F&& body) {
+  Grid<real>* g = as_grid<real>(h, fn);
+  if (!g) return 1;
+  try {
+    body(*g);
+  } catch (const CudaError& e) {
+    return fail("%s: %s", fn, e.what.c_str());
+  }
+  return 0;
+}
+
+template <typename real>
+int run_impl(lbm_gpu* h, int n_steps, real* av_out, double* sums_out, const char* fn) {
+  if (n_steps < 0) return fail("%s: negative step count", fn);
+  return guarded<real>(h, fn, [&](Grid<real>& g) {
+    std::vector<double> sums;
+    double* sp = sums_out;
+    if (!sp && av_out) { sums.resize(std::max(n_steps, 1)); sp = sums.data(); }
+    g.run(n_steps, sp);
+    if (av_out) {
+      const double div = (double)g.divisor();
+      for (int t = 0; t < n_steps; t++) av_out[t] = (real)(sp[t] / div);
+    }
+  });
+}
+
+}  // namespace
+
+// ======================================================================= C-ABI ====
+extern "C" {
+
+int lbm_gpu_abi_version(void) { return 1; }
+
+const char* lbm_gpu_last_error(void) { return g_error.c_str(); }
+
+int lbm_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
+int lbm_gpu_create(const lbm_param* params, const float* cells_aos, const void* obstacles, int n_gpus,
+                   const int* device_ids, unsigned flags, lbm_gpu** out) {
+  return create_impl<float>(params, cells_aos, obstacles, n_gpus, device_ids, flags, out);
+}
+int lbm_gpu_create_f64(const lbm_param_f64* params, const double* cells_aos, const void* obstacles, int n_gpus,
+                       const int* device_ids, unsigned flags, lbm_gpu** out) {
+  return create_impl<double>(params, cells_aos, obstacles, n_gpus, device_ids, flags, out);
+}
+
+int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows, int device,
+                        const float* cells_aos_rows, const void* obstacles_rows, unsigned flags, lbm_gpu** out) {
+  if (!params || !out) return fail("lbm_gpu_create_slab: NULL argument");
+  *out = nullptr;
+  if (params->nx < 1 || params->ny < 2) return fail("lbm_gpu_create_slab: need nx >= 1 and ny >= 2");
+  if (row0 < 0 || nrows < 1 || row0 + nrows > params->ny) return fail("lbm_gpu_create_slab: rows [%lld,%lld) outside the grid", row0, row0 + nrows);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail("lbm_gpu_create_slab: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail("lbm_gpu_create_slab: device %d not available (%d visible)", device, ndev);
+  std::unique_ptr<Grid<float>> g(new Grid<float>());
+  try {
+    g->prm = *params;
+    g->flags = flags;
+    g->slab_mode = true;
+    g->setup_geometry(params->nx);
+    g->slabs.resize(1);
+    Slab<float>& s = g->slabs[0];
+    s.device = device;
+    s.row0 = row0;
+    s.rows = (int)nrows;
+    const long long ar = (long long)params->ny - 2;
+    s.accel_row = (ar >= row0 && ar < row0 + nrows) ? (int)(ar - row0) + 1 : -1;
+    g->alloc_slab(s);
+    g->load_slab(s, cells_aos_rows, obstacles_rows, 0);
+    if (nrows == params->ny) { g->connect_local(); g->prepare(); }   // whole grid in one slab
+  } catch (const CudaError& e) {
+    return fail("lbm_gpu_create_slab: %s", e.what.c_str());
+  }
+  *out = reinterpret_cast<lbm_gpu*>(static_cast<GridBase*>(g.release()));
+  return 0;
+}
+
+int lbm_gpu_ipc_export(lbm_gpu* h, void* desc) {
+  if (!desc) return fail("lbm_gpu_ipc_export: NULL descriptor");
+  return guarded<float>(h, "lbm_gpu_ipc_export", [&](Grid<float>& g) {
+    if (g.slabs.size() != 1) throw CudaError{"only a one-slab handle can be exported"};
+    Slab<float>& s = g.slabs[0];
+    CK(cudaSetDevice(s.device));
+    IpcDesc d;
+    memset(&d, 0, sizeof d);
+    d.magic = kIpcMagic;
+    d.elem_size = 4;
+    d.device = s.device;
+    d.pid = (int32_t)getpid();
+    d.nx = g.prm.nx; d.pitch = g.pitch; d.rows = s.rows;
+    d.row0 = s.row0;
+    d.plane_stride = g.plane_stride(s);
+    d.base_addr = (unsigned long long)(uintptr_t)s.base;
+    d.off_lattice[0] = s.off_lattice[0]; d.off_lattice[1] = s.off_lattice[1];
+    d.off_sync = s.off_sync;
+    d.steps_done = (unsigned long long)g.steps_done;
+    CK(cudaIpcGetMemHandle(&d.handle, s.base));
+    memset(desc, 0, LBM_GPU_IPC_DESC_BYTES);
+    memcpy(desc, &d, sizeof d);
+  });
+}
+
+int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_above) {
+  if (!desc_below || !desc_above) return fail("lbm_gpu_ipc_connect: NULL descriptor");
+  return guarded<float>(h, "lbm_gpu_ipc_connect", [&](Grid<float>& g) {
+    if (g.slabs.size() != 1) throw CudaError{"only a one-slab handle can be connected"};
+    Slab<float>& s = g.slabs[0];
+    CK(cudaSetDevice(s.device));
+    IpcDesc dn, up;
+    memcpy(&dn, desc_below, sizeof dn);
+    memcpy(&up, desc_above, sizeof up);
+    const long long ny = g.prm.ny;
+    for (const IpcDesc* d : {&dn, &up}) {
+      if (d->magic != kIpcMagic || d->elem_size != 4) throw CudaError{"bad neighbour descriptor"};
+      if (d->nx != g.prm.nx || d->pitch != g.pitch) throw CudaError{"neighbour descriptor is for another grid width"};
+      if (d->steps_done != (unsigned long long)g.steps_done) throw CudaError{"neighbour is at a different timestep"};
+    }
+    if ((dn.row0 + dn.rows) % ny != s.row0 % ny) throw CudaError{"descriptor 'below' does not hold row0-1"};
+    if ((s.row0 + s.rows) % ny != up.row0 % ny) throw CudaError{"descriptor 'above' does not hold row0+nrows"};
+    auto map = [&](const IpcDesc& d, int slot) -> char* {
+      if (d.pid == (int32_t)getpid() && d.base_addr == (unsigned long long)(uintptr_t)s.base) return s.base;
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, d.handle, cudaIpcMemLazyEnablePeerAccess));
+      s.ipc_mapped[slot] = p;
+      return (char*)p;
+    };
+    char* dn_base = map(dn, 0);
+    char* up_base = (memcmp(&dn.handle, &up.handle, sizeof dn.handle) == 0 && dn.pid == up.pid) ? dn_base : map(up, 1);
+    for (int b = 0; b < 2; b++) {
+      s.dn_lattice[b] = (float*)(dn_base + dn.off_lattice[b]);
+      s.up_lattice[b] = (float*)(up_base + up.off_lattice[b]);
+    }
+    s.dn_plane_stride = dn.plane_stride;
+    s.up_plane_stride = up.plane_stride;
+    s.dn_rows = dn.rows;
+    s.dn_flag = (unsigned long long*)(dn_base + dn.off_sync) + kFlagFromAbove;
+    s.up_flag = (unsigned long long*)(up_base + up.off_sync) + kFlagFromBelow;
+    g.multi = true;
+    g.connected = true;
+  });
+}
+
+int lbm_gpu_ipc_prepare(lbm_gpu* h) {
+  return guarded<float>(h, "lbm_gpu_ipc_prepare", [&](Grid<float>& g) { g.prepare(); });
+}
+
+int lbm_gpu_run(lbm_gpu* h, int n_steps, float* av_vels_out) {
+  return run_impl<float>(h, n_steps, av_vels_out, nullptr, "lbm_gpu_run");
+}
+int lbm_gpu_run_f64(lbm_gpu* h, int n_steps, double* av_vels_out) {
+  return run_impl<double>(h, n_steps, av_vels_out, nullptr, "lbm_gpu_run_f64");
+}
+int lbm_gpu_run_sums(lbm_gpu* h, int n_steps, double* sums_out) {
+  if (!h) return fail("lbm_gpu_run_sums: NULL handle");
+  if (reinterpret_cast<GridBase*>(h)->is_f64()) return run_impl<double>(h, n_steps, nullptr, sums_out, "lbm_gpu_run_sums");
+  return run_impl<float>(h, n_steps, nullptr, sums_out, "lbm_gpu_run_sums");
+}
+
+int lbm_gpu_set_global_free_cells(lbm_gpu* h, long long free_cells) {
+  if (!h) return fail("lbm_gpu_set_global_free_cells: NULL handle");
+  if (free_cells < 1) return fail("lbm_gpu_set_global_free_cells: count must be positive");
+  GridBase* b = reinterpret_cast<GridBase*>(h);
+  if (b->is_f64()) static_cast<Grid<double>*>(b)->global_free_cells = free_cells;
+  else static_cast<Grid<float>*>(b)->global_free_cells = free_cells;
+  return 0;
+}
+
+int lbm_gpu_download(lbm_gpu* h, float* out) {
+  if (!out) return fail("lbm_gpu_download: NULL output");
+  return guarded<float>(h, "lbm_gpu_download", [&](Grid<float>& g) {
+    long long rows = 0;
+    for (auto& s : g.slabs) rows += s.rows;
+    g.download_rows(g.slabs[0].row0, rows, out);
+  });
+}
+int lbm_gpu_download_f64(lbm_gpu* h, double* out) {
+  if (!out) return fail("lbm_gpu_download_f64: NULL output");
+  return guarded<double>(h, "lbm_gpu_download_f64", [&](Grid<double>& g) {
+    long long rows = 0;
+    for (auto& s : g.slabs) rows += s.rows;
+    g.download_rows(g.slabs[0].row0, rows, out);
+  });
+}
+int lbm_gpu_download_rows(lbm_gpu* h, long long row0, long long nrows, float* out) {
+  if (!out || nrows < 0) return fail("lbm_gpu_download_rows: bad argument");
+  return guarded<float>(h, "lbm_gpu_download_rows", [&](Grid<float>& g) { g.download_rows(row0, nrows, out); });
+}
+
+int lbm_gpu_final_fields(lbm_gpu* h, long long row0, long long nrows, float* ux, float* uy, float* u, float* p) {
+  if (nrows < 0) return fail("lbm_gpu_final_fields: bad argument");
+  return guarded<float>(h, "lbm_gpu_final_fields", [&](Grid<float>& g) { g.final_fields(row0, nrows, ux, uy, u, p); });
+}
+int lbm_gpu_final_fields_f64(lbm_gpu* h, long long row0, long long nrows, double* ux, double* uy, double* u, double* p) {
+  if (nrows < 0) return fail("lbm_gpu_final_fields_f64: bad argument");
+  return guarded<double>(h, "lbm_gpu_final_fields_f64", [&](Grid<double>& g) { g.final_fields(row0, nrows, ux, uy, u, p); });
+}
+
+int lbm_gpu_av_velocity(lbm_gpu* h, float* av_out) {
+  if (!av_out) return fail("lbm_gpu_av_velocity: NULL output");
+  return guarded<float>(h, "lbm_gpu_av_velocity", [&](Grid<float>& g) {
+    *av_out = (float)(g.av_velocity_sum() / (double)g.divisor());
+  });
+}
+int lbm_gpu_av_velocity_f64(lbm_gpu* h, double* av_out) {
+  if (!av_out) return fail("lbm_gpu_av_velocity_f64: NULL output");
+  return guarded<double>(h, "lbm_gpu_av_velocity_f64", [&](Grid<double>& g) {
+    *av_out = g.av_velocity_sum() / (double)g.divisor();
+  });
+}
+
+int lbm_gpu_upload(lbm_gpu* h, const float* cells_aos) {
+  if (!cells_aos) return fail("lbm_gpu_upload: NULL input");
+  return guarded<float>(h, "lbm_gpu_upload", [&](Grid<float>& g) {
+    const int cur = (int)(g.steps_done & 1);
+    const long long base = g.slabs[0].row0;
+    for (auto& s : g.slabs) g.upload_cells(s, cells_aos + (size_t)(s.row0 - base) * g.prm.nx * 9, cur);
+    if (!g.slab_mode || g.slabs[0].rows == g.prm.ny) g.prepare();
+  });
+}
+int lbm_gpu_upload_f64(lbm_gpu* h, const double* cells_aos) {
+  if (!cells_aos) return fail("lbm_gpu_upload_f64: NULL input");
+  return guarded<double>(h, "lbm_gpu_upload_f64", [&](Grid<double>& g) {
+    const int cur = (int)(g.steps_done & 1);
+    for (auto& s : g.slabs) g.upload_cells(s, cells_aos + (size_t)s.row0 * g.prm.nx * 9, cur);
+    g.prepare();
+  });
+}
+
+int lbm_gpu_get_info(lbm_gpu* h, lbm_gpu_info* info) {
+  if (!h || !info) return fail("lbm_gpu_get_info: NULL argument");
+  memset(info, 0, sizeof *info);
+  GridBase* b = reinterpret_cast<GridBase*>(h);
+  auto fill = [&](auto& g) {
+    info->nx = g.prm.nx; info->ny = g.prm.ny;
+    info->n_gpus = (int)g.slabs.size();
+    info->is_f64 = g.is_f64();
+    info->kernel = g.kernel;
+    info->pitch = g.pitch;
+    info->local_free_cells = g.local_free_cells();
+    info->free_cells = g.divisor();
+    info->local_row0 = g.slabs[0].row0;
+    long long rows = 0;
+    size_t bytes = 0;
+    for (auto& s : g.slabs) { rows += s.rows; bytes = std::max(bytes, s.bytes + kStagingBytes); }
+    info->local_rows = rows;
+    info->steps_done = g.steps_done;
+    info->kernel_launches = g.launches;
+    info->last_run_device_ms = g.last_run_ms;
+    info->last_step_kernel_ms = g.last_step_ms;
+    info->device_bytes = bytes;
+  };
+  if (b->is_f64()) fill(*static_cast<Grid<double>*>(b));
+  else fill(*static_cast<Grid<float>*>(b));
+  return 0;
+}
+
+int lbm_gpu_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail("lbm_gpu_host_alloc: NULL argument");
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("lbm_gpu_host_alloc: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+void lbm_gpu_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+void lbm_gpu_destroy(lbm_gpu* h) {
+  if (!h) return;
+  delete reinterpret_cast<GridBase*>(h);
+}
+
+}  // extern "C"

@@ -1,0 +1,651 @@
+// lbm_kernels.cuh -- sm_100a device code of the d2q9-bgk timestep loop.
+//
+// One fused kernel per timestep does what the reference's timestep_new2 does
+// (d2q9-bgk.c:228-1813): accelerate_flow (:229-260), pull-propagate (:990-998),
+// rebound (:971-981), BGK collision (:983-1100) and the av_velocity contribution
+// (:1103-1130), plus -- new here -- the halo push into the neighbouring slabs.
+//
+// Data layout in HBM (one "slab" = the rows one GPU holds):
+//   lattice  2 buffers x 9 planes x (rows+2) x pitch   structure-of-arrays; local row 0
+//            and rows+1 are ghost rows holding the neighbours' edge rows (periodic in y,
+//            so with one slab they hold the slab's own opposite edge);
+//   mask     rows x pitch/32 uint32, bit = 1 for an obstacle cell;
+//   side     2 x 6 x pitch: row ny-2 of planes 1,3,5,6,7,8 AFTER accelerate_flow.
+//            The lattice itself always holds the un-accelerated state; readers that
+//            pull from row ny-2 take those six planes from `side` instead.  This is
+//            the same arithmetic as accelerating in place before streaming
+//            (d2q9-bgk.c:229-260) without a separate kernel or a pre-pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lbm {
+
+// ------------------------------------------------------------------------------------
+// arithmetic policy: STRICT mirrors the reference's C expression trees with
+// round-to-nearest single operations (never contracted into FMA) so the result is
+// bit-identical to a gcc -O2 -ffp-contract=off build; the default lets the compiler
+// contract and uses an algebraically equal, cheaper form of the equilibrium.
+// ------------------------------------------------------------------------------------
+template <typename real, bool STRICT> struct Ops;
+
+template <> struct Ops<float, true> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+template <> struct Ops<double, true> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+template <> struct Ops<float, false> {
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+  static __device__ __forceinline__ float sqrt(float a) { return sqrtf(a); }
+};
+template <> struct Ops<double, false> {
+  static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+  static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+  static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+  static __device__ __forceinline__ double sqrt(double a) { return ::sqrt(a); }
+};
+
+// |u| is accumulated as an exact 128-bit fixed-point sum (unit 2^-52): integer adds
+// are associative, so the per-step average does not depend on block scheduling, grid
+// shape or on how the rows are split over GPUs.
+#define LBM_FIX_SCALE 4503599627370496.0 /* 2^52 */
+__device__ __forceinline__ unsigned long long to_fixed(float s) {
+  return __float2ull_rn(s * 4503599627370496.0f);
+}
+__device__ __forceinline__ unsigned long long to_fixed(double s) {
+  return __double2ull_rn(s * 4503599627370496.0);
+}
+
+// ------------------------------------------------------------------------------------
+// one cell: p[0..8] pulled values -> o[0..8] stored values, returns |u| of the stored
+// values (0 for an obstacle cell).
+// ------------------------------------------------------------------------------------
+template <typename real, bool STRICT>
+__device__ __forceinline__ real cell_update(const real (&p)[9], const bool obstacle, const real omega,
+                                            real (&o)[9]) {
+  typedef Ops<real, STRICT> M;
+  real c[9];
+  real speed;
+  if (STRICT) {
+    // d2q9-bgk.c:983-1100, expression trees as written there
+    const real c_sq = (real)1 / (real)3;
+    const real w0 = (real)4 / (real)9;
+    const real w1 = (real)1 / (real)9;
+    const real w2 = (real)1 / (real)36;
+    const real two_csq = (real)2 * c_sq;
+    const real two_csq_csq = (real)2 * c_sq * c_sq;
+    real rho = M::add((real)0, p[0]);
+#pragma unroll
+    for (int k = 1; k < 9; k++) rho = M::add(rho, p[k]);
+    const real ux = M::div(M::sub(M::add(M::add(p[1], p[5]), p[8]), M::add(M::add(p[3], p[6]), p[7])), rho);
+    const real uy = M::div(M::sub(M::add(M::add(p[2], p[5]), p[6]), M::add(M::add(p[4], p[7]), p[8])), rho);
+    const real usq = M::add(M::mul(ux, ux), M::mul(uy, uy));
+    real u[9];
+    u[1] = ux;                 u[2] = uy;
+    u[3] = -ux;                u[4] = -uy;
+    u[5] = M::add(ux, uy);     u[6] = M::add(-ux, uy);
+    u[7] = M::sub(-ux, uy);    u[8] = M::sub(ux, uy);
+    const real t_usq = M::div(usq, two_csq);
+    real d[9];
+    d[0] = M::mul(M::mul(w0, rho), M::sub((real)1, t_usq));
+#pragma unroll
+    for (int k = 1; k < 9; k++) {
+      const real w = (k < 5) ? w1 : w2;
+      const real poly = M::sub(M::add(M::add((real)1, M::div(u[k], c_sq)),
+                                      M::div(M::mul(u[k], u[k]), two_csq_csq)), t_usq);
+      d[k] = M::mul(M::mul(w, rho), poly);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) c[k] = M::add(p[k], M::mul(omega, M::sub(d[k], p[k])));
+    // d2q9-bgk.c:1103-1128: velocity recomputed from the values just stored
+    real rho2 = M::add((real)0, c[0]);
+#pragma unroll
+    for (int k = 1; k < 9; k++) rho2 = M::add(rho2, c[k]);
+    const real vx = M::div(M::sub(M::add(M::add(c[1], c[5]), c[8]), M::add(M::add(c[3], c[6]), c[7])), rho2);
+    const real vy = M::div(M::sub(M::add(M::add(c[2], c[5]), c[6]), M::add(M::add(c[4], c[7]), c[8])), rho2);
+    speed = M::sqrt(M::add(M::mul(vx, vx), M::mul(vy, vy)));
+  } else {
+    // same maths, cheaper form: one reciprocal, 1/c_sq = 3, 1/(2 c_sq^2) = 4.5,
+    // 1/(2 c_sq) = 1.5; the compiler is free to contract into FMA.
+    const real w0 = (real)(4.0 / 9.0), w1 = (real)(1.0 / 9.0), w2 = (real)(1.0 / 36.0);
+    const real e = (p[1] + p[5]) + p[8];
+    const real w = (p[3] + p[6]) + p[7];
+    const real n = (p[2] + p[5]) + p[6];
+    const real s = (p[4] + p[7]) + p[8];
+    const real rho = ((p[0] + p[2]) + (p[4] + e)) + w;
+    const real inv = (real)1 / rho;
+    const real ux = (e - w) * inv;
+    const real uy = (n - s) * inv;
+    const real base = (real)1 - (real)1.5 * (ux * ux + uy * uy);
+    const real r0 = omega * w0 * rho, r1 = omega * w1 * rho, r2 = omega * w2 * rho;
+    const real keep = (real)1 - omega;
+    const real upv = ux + uy, umv = ux - uy;
+#define LBM_EQ(uk) (base + (uk) * ((real)3 + (real)4.5 * (uk)))
+    c[0] = keep * p[0] + r0 * base;
+    c[1] = keep * p[1] + r1 * LBM_EQ(ux);
+    c[2] = keep * p[2] + r1 * LBM_EQ(uy);
+    c[3] = keep * p[3] + r1 * LBM_EQ(-ux);
+    c[4] = keep * p[4] + r1 * LBM_EQ(-uy);
+    c[5] = keep * p[5] + r2 * LBM_EQ(upv);
+    c[6] = keep * p[6] + r2 * LBM_EQ(-umv);
+    c[7] = keep * p[7] + r2 * LBM_EQ(-upv);
+    c[8] = keep * p[8] + r2 * LBM_EQ(umv);
+#undef LBM_EQ
+    const real e2 = (c[1] + c[5]) + c[8];
+    const real w_2 = (c[3] + c[6]) + c[7];
+    const real n2 = (c[2] + c[5]) + c[6];
+    const real s2 = (c[4] + c[7]) + c[8];
+    const real rho2 = ((c[0] + c[2]) + (c[4] + e2)) + w_2;
+    const real inv2 = (real)1 / rho2;
+    const real vx = (e2 - w_2) * inv2;
+    const real vy = (n2 - s2) * inv2;
+    speed = Ops<real, false>::sqrt(vx * vx + vy * vy);
+  }
+  // obstacle: bounce-back of the pulled values (d2q9-bgk.c:971-981), no average
+  o[0] = obstacle ? p[0] : c[0];
+  o[1] = obstacle ? p[3] : c[1];
+  o[2] = obstacle ? p[4] : c[2];
+  o[3] = obstacle ? p[1] : c[3];
+  o[4] = obstacle ? p[2] : c[4];
+  o[5] = obstacle ? p[7] : c[5];
+  o[6] = obstacle ? p[8] : c[6];
+  o[7] = obstacle ? p[5] : c[7];
+  o[8] = obstacle ? p[6] : c[8];
+  return obstacle ? (real)0 : speed;
+}
+
+// accelerate_flow on one cell's speeds (d2q9-bgk.c:246-258); a[] = {f1,f3,f5,f6,f7,f8}.
+template <typename real, bool STRICT>
+__device__ __forceinline__ void cell_accelerate(real& f1, real& f3, real& f5, real& f6, real& f7, real& f8,
+                                                const bool obstacle, const real aw1, const real aw2) {
+  typedef Ops<real, true> M;   // single adds/subs: nothing to contract, always exact ops
+  const bool go = !obstacle && M::sub(f3, aw1) > (real)0 && M::sub(f6, aw2) > (real)0 &&
+                  M::sub(f7, aw2) > (real)0;
+  if (go) {
+    f1 = M::add(f1, aw1); f5 = M::add(f5, aw2); f8 = M::add(f8, aw2);
+    f3 = M::sub(f3, aw1); f6 = M::sub(f6, aw2); f7 = M::sub(f7, aw2);
+  }
+}
+
+// |u| etc. of a stored cell (d2q9-bgk.c:2681-2705 / :2948-2972), reference tree order.
+template <typename real>
+__device__ __forceinline__ real cell_macroscopic(const real (&f)[9], real& ux, real& uy, real& rho) {
+  typedef Ops<real, true> M;
+  rho = M::add((real)0, f[0]);
+#pragma unroll
+  for (int k = 1; k < 9; k++) rho = M::add(rho, f[k]);
+  ux = M::div(M::sub(M::add(M::add(f[1], f[5]), f[8]), M::add(M::add(f[3], f[6]), f[7])), rho);
+  uy = M::div(M::sub(M::add(M::add(f[2], f[5]), f[6]), M::add(M::add(f[4], f[7]), f[8])), rho);
+  return M::sqrt(M::add(M::mul(ux, ux), M::mul(uy, uy)));
+}
+
+// ------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------
+template <typename real>
+struct StepArgs {
+  const real* src;             // lattice buffer read this step (plane 0, local row 0)
+  real* dst;                   // lattice buffer written this step
+  const real* side_src;        // accelerated row ny-2, planes {1,3,5,6,7,8} x pitch (read)
+  real* side_dst;              // same, written for the next step
+  const uint32_t* mask;        // rows x mask_pitch words
+  unsigned long long* av_lo;   // this step's 128-bit |u| sum, low / high word
+  unsigned long long* av_hi;
+  // halo push targets: ghost rows of the neighbours' dst buffers (plane 0 of that row)
+  real* up_ghost;              // neighbour above: its local row 0
+  real* dn_ghost;              // neighbour below: its local row rows'+1
+  long long up_plane_stride;   // plane strides of the neighbours' lattices
+  long long dn_plane_stride;
+  // cross-slab ordering (only when MULTI)
+  volatile unsigned long long* flag_from_below;  // local: steps completed by neighbour below
+  volatile unsigned long long* flag_from_above;
+  unsigned long long* up_flag;                   // neighbour above's flag_from_below
+  unsigned long long* dn_flag;                   // neighbour below's flag_from_above
+  unsigned long long* boundary_done;             // local counter of finished boundary blocks
+  unsigned long long step;                       // global index of this step (0-based)
+  long long plane_stride;      // (rows+2) * pitch
+  int nx;
+  int rows;                    // local rows (R)
+  int pitch;                   // elements per row, multiple of 32
+  int mask_pitch;              // words per mask row
+  int accel_row;               // local row (1-based) holding global row ny-2, or -1
+  int tiles_x, tiles_y;
+  real omega;
+  real aw1, aw2;               // density*accel/9, density*accel/36 (d2q9-bgk.c:230-231)
+};
+
+template <typename real> struct alignas(4 * sizeof(real)) Vec4 { real x, y, z, w; };
+
+template <typename real>
+__device__ __forceinline__ Vec4<real> ld4(const real* p) { return *reinterpret_cast<const Vec4<real>*>(p); }
+template <typename real>
+__device__ __forceinline__ void st4(real* p, const Vec4<real>& v) { *reinterpret_cast<Vec4<real>*>(p) = v; }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const volatile unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// block-wide exact sum of per-thread fixed-point |u| -> one 128-bit atomic accumulate
+__device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned long long* lo,
+                                                 unsigned long long* hi) {
+  __shared__ unsigned long long warp_sums[32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+  if ((tid & 31) == 0) warp_sums[tid >> 5] = q;
+  __syncthreads();
+  if (tid < 32) {
+    unsigned long long v = (tid < nwarps) ? warp_sums[tid] : 0ULL;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (tid == 0 && v != 0ULL) {
+      const unsigned long long old = atomicAdd(lo, v);
+      if (old + v < old) atomicAdd(hi, 1ULL);
+    }
+  }
+}
+
+// Block -> tile mapping.  The row tiles that touch the slab's first and last row are
+// given the lowest block indices so that they are dispatched first: their halo pushes
+// leave early and the neighbours' next step never waits for them.
+__device__ __forceinline__ void tile_of_block(const int tiles_x, const int tiles_y, int& tx, int& ty) {
+  const unsigned b = blockIdx.x;
+  const unsigned slot = b / (unsigned)tiles_x;
+  tx = (int)(b - slot * (unsigned)tiles_x);
+  if (slot == 0) ty = 0;
+  else if (slot == 1) ty = tiles_y - 1;
+  else ty = (int)slot - 1;
+}
+
+template <typename real, bool MULTI>
+__device__ __forceinline__ void boundary_wait(const StepArgs<real>& a, const bool is_boundary) {
+  if (MULTI && is_boundary) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      while (ld_acquire_sys(a.flag_from_below) < a.step) { }
+      while (ld_acquire_sys(a.flag_from_above) < a.step) { }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename real, bool MULTI>
+__device__ __forceinline__ void boundary_signal(const StepArgs<real>& a, const bool is_boundary) {
+  if (MULTI && is_boundary) {
+    __threadfence_system();            // this thread's halo pushes are visible system-wide
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      const unsigned long long nb = (unsigned long long)a.tiles_x * (a.tiles_y > 1 ? 2ULL : 1ULL);
+      const unsigned long long old = atomicAdd(a.boundary_done, 1ULL);
+      if (old + 1ULL == nb * (a.step + 1ULL)) {
+        __threadfence_system();
+        st_release_sys(a.up_flag, a.step + 1ULL);
+        st_release_sys(a.dn_flag, a.step + 1ULL);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K1a  lbm_step_vec4: four cells per thread, 128-bit loads/stores straight from/to the
+// SoA planes (nx % 4 == 0).  x-shifted planes come from the aligned vector plus one
+// element of the neighbouring lane (warp shuffle); the two edge lanes of a warp fetch
+// that element with a scalar load that also implements the periodic wrap in x.
+// blockDim = (BX, BY), BX a multiple of 32 so that a warp never spans two rows.
+// ------------------------------------------------------------------------------------
+template <typename real, bool STRICT, bool MULTI>
+__global__ void __launch_bounds__(256)
+lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
+  int tx, ty;
+  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  boundary_wait<real, MULTI>(a, is_boundary);
+
+  const int x0 = (tx * (int)blockDim.x + (int)threadIdx.x) * 4;
+  const int r = 1 + ty * (int)blockDim.y + (int)threadIdx.y;    // local row, 1-based
+  const bool active = (x0 < a.nx) && (r <= a.rows);
+  const int lane = threadIdx.x & 31;
+  unsigned long long q = 0ULL;
+
+  // clamp so that inactive threads still form valid addresses (they take part in the
+  // shuffles but never store)
+  const int xc = active ? x0 : 0;
+  const int rc = active ? r : 1;
+  const long long PS = a.plane_stride;
+  const long long oC = (long long)rc * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
+
+  // planes 1,3 of the centre row / 5,6 of the south row / 7,8 of the north row come
+  // from the accelerated side row when that row is global row ny-2
+  const bool cA = (rc == a.accel_row), sA = (rc - 1 == a.accel_row), nA = (rc + 1 == a.accel_row);
+  const real* p0 = a.src + oC;
+  const real* p1 = cA ? a.side_src + 0 * a.pitch : a.src + 1 * PS + oC;
+  const real* p2 = a.src + 2 * PS + oS;
+  const real* p3 = cA ? a.side_src + 1 * a.pitch : a.src + 3 * PS + oC;
+  const real* p4 = a.src + 4 * PS + oN;
+  const real* p5 = sA ? a.side_src + 2 * a.pitch : a.src + 5 * PS + oS;
+  const real* p6 = sA ? a.side_src + 3 * a.pitch : a.src + 6 * PS + oS;
+  const real* p7 = nA ? a.side_src + 4 * a.pitch : a.src + 7 * PS + oN;
+  const real* p8 = nA ? a.side_src + 5 * a.pitch : a.src + 8 * PS + oN;
+
+  // edge elements first (scalar, predicated), then the nine aligned vectors
+  const bool need_w = (lane == 0) || (xc == 0);
+  const bool need_e = (lane == 31) || (xc + 4 >= a.nx);
+  const int xw = (xc == 0) ? a.nx - 1 : xc - 1;
+  const int xe = (xc + 4 >= a.nx) ? 0 : xc + 4;
+  real w1e = 0, w5e = 0, w8e = 0, e3e = 0, e6e = 0, e7e = 0;
+  if (need_w) { w1e = p1[xw]; w5e = p5[xw]; w8e = p8[xw]; }
+  if (need_e) { e3e = p3[xe]; e6e = p6[xe]; e7e = p7[xe]; }
+
+  const Vec4<real> v0 = ld4(p0 + xc), v1 = ld4(p1 + xc), v2 = ld4(p2 + xc), v3 = ld4(p3 + xc),
+                   v4 = ld4(p4 + xc), v5 = ld4(p5 + xc), v6 = ld4(p6 + xc), v7 = ld4(p7 + xc),
+                   v8 = ld4(p8 + xc);
+  const uint32_t mword = a.mask[(long long)(rc - 1) * a.mask_pitch + (xc >> 5)];
+  const uint32_t mbits = (mword >> (xc & 31)) & 0xFu;
+
+  // element x0-1 of planes 1,5,8 and x0+4 of planes 3,6,7 from the neighbouring lanes
+  real l1 = __shfl_up_sync(0xffffffffu, v1.w, 1), l5 = __shfl_up_sync(0xffffffffu, v5.w, 1),
+       l8 = __shfl_up_sync(0xffffffffu, v8.w, 1);
+  real r3 = __shfl_down_sync(0xffffffffu, v3.x, 1), r6 = __shfl_down_sync(0xffffffffu, v6.x, 1),
+       r7 = __shfl_down_sync(0xffffffffu, v7.x, 1);
+  if (need_w) { l1 = w1e; l5 = w5e; l8 = w8e; }
+  if (need_e) { r3 = e3e; r6 = e6e; r7 = e7e; }
+
+  real in[4][9], out[4][9];
+  in[0][0] = v0.x; in[1][0] = v0.y; in[2][0] = v0.z; in[3][0] = v0.w;
+  in[0][1] = l1;   in[1][1] = v1.x; in[2][1] = v1.y; in[3][1] = v1.z;
+  in[0][2] = v2.x; in[1][2] = v2.y; in[2][2] = v2.z; in[3][2] = v2.w;
+  in[0][3] = v3.y; in[1][3] = v3.z; in[2][3] = v3.w; in[3][3] = r3;
+  in[0][4] = v4.x; in[1][4] = v4.y; in[2][4] = v4.z; in[3][4] = v4.w;
+  in[0][5] = l5;   in[1][5] = v5.x; in[2][5] = v5.y; in[3][5] = v5.z;
+  in[0][6] = v6.y; in[1][6] = v6.z; in[2][6] = v6.w; in[3][6] = r6;
+  in[0][7] = v7.y; in[1][7] = v7.z; in[2][7] = v7.w; in[3][7] = r7;
+  in[0][8] = l8;   in[1][8] = v8.x; in[2][8] = v8.y; in[3][8] = v8.z;
+
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const real s = cell_update<real, STRICT>(in[j], (mbits >> j) & 1u, a.omega, out[j]);
+    q += to_fixed(s);
+  }
+
+  if (active) {
+    real* d = a.dst + oC + xc;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      Vec4<real> v; v.x = out[0][k]; v.y = out[1][k]; v.z = out[2][k]; v.w = out[3][k];
+      st4(d + k * PS, v);
+    }
+    const bool first = (r == 1), last = (r == a.rows), acc = (r == a.accel_row);
+    if (first | last | acc) {         // warp-uniform: a warp never spans two rows
+      if (acc) {
+        // next step's accelerate_flow on the row just produced (d2q9-bgk.c:229-260)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          cell_accelerate<real, STRICT>(out[j][1], out[j][3], out[j][5], out[j][6], out[j][7], out[j][8],
+                                        (mbits >> j) & 1u, a.aw1, a.aw2);
+        const int ks[6] = {1, 3, 5, 6, 7, 8};
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
+          st4(a.side_dst + (long long)i * a.pitch + xc, v);
+        }
+      }
+      if (first) {                    // speeds 4,7,8 are pulled by the row below
+        const int ks[3] = {4, 7, 8};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
+          st4(a.dn_ghost + ks[i] * a.dn_plane_stride + xc, v);
+        }
+      }
+      if (last) {                     // speeds 2,5,6 are pulled by the row above
+        const int ks[3] = {2, 5, 6};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
+          st4(a.up_ghost + ks[i] * a.up_plane_stride + xc, v);
+        }
+      }
+    }
+  } else {
+    q = 0ULL;
+  }
+  block_accumulate(q, a.av_lo, a.av_hi);
+  boundary_signal<real, MULTI>(a, is_boundary);
+}
+
+// ------------------------------------------------------------------------------------
+// K1b  lbm_step_scalar: one cell per thread, any nx.  Same arithmetic; used for grids
+// whose width is not a multiple of 4 and as an independent cross-check of K1a.
+// ------------------------------------------------------------------------------------
+template <typename real, bool STRICT, bool MULTI>
+__global__ void __launch_bounds__(256)
+lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
+  int tx, ty;
+  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  boundary_wait<real, MULTI>(a, is_boundary);
+
+  const int x = tx * (int)blockDim.x + (int)threadIdx.x;
+  const int r = 1 + ty * (int)blockDim.y + (int)threadIdx.y;
+  const bool active = (x < a.nx) && (r <= a.rows);
+  unsigned long long q = 0ULL;
+  if (active) {
+    const long long PS = a.plane_stride;
+    const long long oC = (long long)r * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
+    const bool cA = (r == a.accel_row), sA = (r - 1 == a.accel_row), nA = (r + 1 == a.accel_row);
+    const int xw = (x == 0) ? a.nx - 1 : x - 1;
+    const int xe = (x + 1 == a.nx) ? 0 : x + 1;
+    real p[9], o[9];
+    p[0] = a.src[oC + x];
+    p[1] = cA ? a.side_src[0 * a.pitch + xw] : a.src[1 * PS + oC + xw];
+    p[2] = a.src[2 * PS + oS + x];
+    p[3] = cA ? a.side_src[1 * a.pitch + xe] : a.src[3 * PS + oC + xe];
+    p[4] = a.src[4 * PS + oN + x];
+    p[5] = sA ? a.side_src[2 * a.pitch + xw] : a.src[5 * PS + oS + xw];
+    p[6] = sA ? a.side_src[3 * a.pitch + xe] : a.src[6 * PS + oS + xe];
+    p[7] = nA ? a.side_src[4 * a.pitch + xe] : a.src[7 * PS + oN + xe];
+    p[8] = nA ? a.side_src[5 * a.pitch + xw] : a.src[8 * PS + oN + xw];
+    const bool obst = (a.mask[(long long)(r - 1) * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+    const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
+    q = to_fixed(s);
+#pragma unroll
+    for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
+    if (r == a.accel_row) {
+      cell_accelerate<real, STRICT>(o[1], o[3], o[5], o[6], o[7], o[8], obst, a.aw1, a.aw2);
+      a.side_dst[0 * a.pitch + x] = o[1]; a.side_dst[1 * a.pitch + x] = o[3];
+      a.side_dst[2 * a.pitch + x] = o[5]; a.side_dst[3 * a.pitch + x] = o[6];
+      a.side_dst[4 * a.pitch + x] = o[7]; a.side_dst[5 * a.pitch + x] = o[8];
+    }
+    if (r == 1) {
+      a.dn_ghost[4 * a.dn_plane_stride + x] = o[4];
+      a.dn_ghost[7 * a.dn_plane_stride + x] = o[7];
+      a.dn_ghost[8 * a.dn_plane_stride + x] = o[8];
+    }
+    if (r == a.rows) {
+      a.up_ghost[2 * a.up_plane_stride + x] = o[2];
+      a.up_ghost[5 * a.up_plane_stride + x] = o[5];
+      a.up_ghost[6 * a.up_plane_stride + x] = o[6];
+    }
+  }
+  block_accumulate(q, a.av_lo, a.av_hi);
+  boundary_signal<real, MULTI>(a, is_boundary);
+}
+
+// ------------------------------------------------------------------------------------
+// K3  lbm_prepare: run once after the lattice was created or uploaded.  Fills the side
+// row (accelerate_flow applied to row ny-2 of the current buffer, d2q9-bgk.c:229-260)
+// and pushes the slab's edge rows into the neighbours' ghost rows of the same buffer.
+// One thread per column.
+// ------------------------------------------------------------------------------------
+template <typename real>
+struct PrepareArgs {
+  const real* cur;            // current lattice buffer
+  real* side_cur;             // side row of the same parity
+  const uint32_t* mask;
+  real* up_ghost;             // neighbour above's ghost row 0 in its current buffer
+  real* dn_ghost;             // neighbour below's ghost row rows'+1
+  long long up_plane_stride, dn_plane_stride, plane_stride;
+  int nx, rows, pitch, mask_pitch, accel_row;
+  real aw1, aw2;
+};
+
+template <typename real>
+__global__ void lbm_prepare(const PrepareArgs<real> a) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= a.nx) return;
+  const long long PS = a.plane_stride;
+#pragma unroll 1
+  for (int which = 0; which < 3; which++) {
+    // 0: accelerate row -> side; 1: first row -> push down; 2: last row -> push up
+    const int r = (which == 0) ? a.accel_row : (which == 1 ? 1 : a.rows);
+    if (r < 1) continue;
+    const long long o = (long long)r * a.pitch + x;
+    real f[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) f[k] = a.cur[k * PS + o];
+    if (r == a.accel_row) {
+      const bool obst = (a.mask[(long long)(r - 1) * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+      cell_accelerate<real, true>(f[1], f[3], f[5], f[6], f[7], f[8], obst, a.aw1, a.aw2);
+    }
+    if (which == 0) {
+      a.side_cur[0 * a.pitch + x] = f[1]; a.side_cur[1 * a.pitch + x] = f[3];
+      a.side_cur[2 * a.pitch + x] = f[5]; a.side_cur[3 * a.pitch + x] = f[6];
+      a.side_cur[4 * a.pitch + x] = f[7]; a.side_cur[5 * a.pitch + x] = f[8];
+    } else if (which == 1) {
+      a.dn_ghost[4 * a.dn_plane_stride + x] = f[4];
+      a.dn_ghost[7 * a.dn_plane_stride + x] = f[7];
+      a.dn_ghost[8 * a.dn_plane_stride + x] = f[8];
+    } else {
+      a.up_ghost[2 * a.up_plane_stride + x] = f[2];
+      a.up_ghost[5 * a.up_plane_stride + x] = f[5];
+      a.up_ghost[6 * a.up_plane_stride + x] = f[6];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K4  setup / output kernels (not on the per-step path)
+// ------------------------------------------------------------------------------------
+// rest state, d2q9-bgk.c:2802-2823
+template <typename real>
+__global__ void lbm_init_rest(real* buf, long long plane_stride, int pitch, int nx, int rows,
+                              real w0, real w1, real w2) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(rows + 2) * pitch;
+  if (n >= total) return;
+#pragma unroll
+  for (int k = 0; k < 9; k++) buf[k * plane_stride + n] = (k == 0) ? w0 : (k < 5 ? w1 : w2);
+}
+
+// AoS rows (9 reals per cell, dense nx) -> SoA planes; `aos` holds nrows rows that go
+// to local rows [r0, r0+nrows)
+template <typename real>
+__global__ void lbm_aos_to_soa(const real* __restrict__ aos, real* __restrict__ buf, long long plane_stride,
+                               int pitch, int nx, int r0, long long ncells) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncells * 9) return;
+  const long long cell = i / 9;
+  const int k = (int)(i - cell * 9);
+  const long long row = cell / nx;
+  const int x = (int)(cell - row * nx);
+  buf[k * plane_stride + (r0 + row) * pitch + x] = aos[i];
+}
+
+template <typename real>
+__global__ void lbm_soa_to_aos(const real* __restrict__ buf, real* __restrict__ aos, long long plane_stride,
+                               int pitch, int nx, int r0, long long ncells) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncells * 9) return;
+  const long long cell = i / 9;
+  const int k = (int)(i - cell * 9);
+  const long long row = cell / nx;
+  const int x = (int)(cell - row * nx);
+  aos[i] = buf[k * plane_stride + (r0 + row) * pitch + x];
+}
+
+// int-per-cell obstacle rows -> bit mask rows; one warp packs 32 cells with a ballot.
+// Also counts the blocked cells.
+__global__ void lbm_pack_mask(const int* __restrict__ obst, uint32_t* __restrict__ mask, int mask_pitch,
+                              int nx, int r0, int nrows, unsigned long long* blocked_count) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // global warp
+  const int lane = threadIdx.x & 31;
+  const int words_per_row = (nx + 31) >> 5;
+  if (gw >= (long long)nrows * words_per_row) return;
+  const int row = (int)(gw / words_per_row);
+  const int wi = (int)(gw - (long long)row * words_per_row);
+  const int x = wi * 32 + lane;
+  const bool b = (x < nx) && (obst[(long long)row * nx + x] != 0);
+  const uint32_t bits = __ballot_sync(0xffffffffu, b);
+  if (lane == 0) {
+    mask[(long long)(r0 + row) * mask_pitch + wi] = bits;
+    if (bits) atomicAdd(blocked_count, (unsigned long long)__popc(bits));
+  }
+}
+
+// dense bit-packed host rows ((nx+31)/32 words per row) -> pitched mask rows
+__global__ void lbm_copy_mask_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ mask, int mask_pitch,
+                                   int nx, int r0, int nrows, unsigned long long* blocked_count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int words_per_row = (nx + 31) >> 5;
+  if (i >= (long long)nrows * words_per_row) return;
+  const int row = (int)(i / words_per_row);
+  const int wi = (int)(i - (long long)row * words_per_row);
+  uint32_t bits = in[i];
+  const int valid = nx - wi * 32;
+  if (valid < 32) bits &= (1u << valid) - 1u;
+  mask[(long long)(r0 + row) * mask_pitch + wi] = bits;
+  if (bits) atomicAdd(blocked_count, (unsigned long long)__popc(bits));
+}
+
+// write_values' per-cell fields (d2q9-bgk.c:2937-2976) for local rows [r0, r0+nrows):
+// dense nx-wide outputs.  Also usable as av_velocity (d2q9-bgk.c:2665-2714) through
+// the 128-bit accumulator when av_lo != NULL.
+template <typename real>
+__global__ void lbm_fields(const real* __restrict__ buf, const uint32_t* __restrict__ mask,
+                           long long plane_stride, int pitch, int mask_pitch, int nx, int r0, int nrows,
+                           real density, real* __restrict__ ux_out, real* __restrict__ uy_out,
+                           real* __restrict__ u_out, real* __restrict__ p_out,
+                           unsigned long long* av_lo, unsigned long long* av_hi) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long q = 0ULL;
+  if (n < (long long)nrows * nx) {
+    const int row = (int)(n / nx);
+    const int x = (int)(n - (long long)row * nx);
+    const int r = r0 + row;                      // local row, 1-based
+    const bool obst = (mask[(long long)(r - 1) * mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+    real f[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) f[k] = buf[k * plane_stride + (long long)r * pitch + x];
+    real ux, uy, rho;
+    real u = cell_macroscopic<real>(f, ux, uy, rho);
+    const real c_sq = (real)1 / (real)3;
+    real pr = Ops<real, true>::mul(rho, c_sq);
+    if (obst) { ux = 0; uy = 0; u = 0; pr = Ops<real, true>::mul(density, c_sq); }
+    if (ux_out) ux_out[n] = ux;
+    if (uy_out) uy_out[n] = uy;
+    if (u_out) u_out[n] = u;
+    if (p_out) p_out[n] = pr;
+    q = to_fixed(u);
+  }
+  if (av_lo) block_accumulate(q, av_lo, av_hi);
+}
+
+}  // namespace lbm

@@ -1,0 +1,163 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (include/lbm_gpu.h), against
+the CPU oracle on the same seeded inputs.
+
+Bar (tier rules + BASELINE.json north_star):
+  * LBM_GPU_STRICT build of the kernel (source operation order, no FMA): BIT-EXACT
+    lattice after k steps against the oracle (which itself is bit-exact against the
+    reference compiled with -O2 -ffp-contract=off, tests/test_oracle_vs_reference.py);
+  * default (FMA-contracted) kernel: relative difference per speed <= 2e-5 after 50
+    steps -- float arithmetic, so not bit-exact; the reference's own -Ofast build
+    differs from its -O2 build by the same order ("fp32 chaos");
+  * av_vels: |gpu - oracle(double accumulation)| <= 1e-6 relative (strict: 1e-7).
+"""
+import numpy as np
+import pytest
+
+import lbm_b200 as L
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
+
+SHAPES = [
+    (128, 128), (128, 256), (256, 64), (64, 7), (4, 2), (8, 3), (36, 5), (132, 9),
+    (1024, 17), (2048, 6),
+]
+ODD_SHAPES = [(1, 2), (3, 5), (37, 11), (129, 4), (250, 9), (33, 2)]
+
+
+def _kernels_for(nx):
+    return [L.KERNEL_SCALAR] + ([L.KERNEL_VEC4] if nx % 4 == 0 else [])
+
+
+@pytest.mark.parametrize("nx,ny", SHAPES + ODD_SHAPES)
+@pytest.mark.parametrize("steps", [1, 2, 10])
+def test_strict_bit_exact(nx, ny, steps):
+    cells, obst = O.random_lattice(nx, ny, seed=nx * 1000 + ny)
+    ref, av_ref, av_ref_d = O.run(cells, obst, steps, DENSITY, ACCEL, OMEGA)
+    for k in _kernels_for(nx):
+        with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=L.STRICT | k) as lat:
+            av = lat.run(steps)
+            got = lat.download()
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), \
+            "kernel %d %dx%d: %d cells differ" % (k, nx, ny, np.count_nonzero((got != ref).any(axis=2)))
+        np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
+
+
+@pytest.mark.parametrize("nx,ny", [(128, 128), (256, 64), (132, 9), (37, 11)])
+def test_fast_kernel_tolerance(nx, ny):
+    steps = 50
+    cells, obst = O.random_lattice(nx, ny, seed=7)
+    ref, _, av_ref_d = O.run(cells, obst, steps, DENSITY, ACCEL, OMEGA)
+    for k in _kernels_for(nx):
+        with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
+            av = lat.run(steps)
+            got = lat.download()
+        rel = np.abs(got.astype(np.float64) - ref) / np.abs(ref)
+        assert rel.max() <= 2e-5, "kernel %d: max rel %.3g" % (k, rel.max())
+        np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-5, atol=0)
+
+
+def test_rest_state_and_obstacle_bits():
+    """cells=NULL generates the reference's rest state on the device (d2q9-bgk.c:2802-2823);
+    the packed-bit obstacle format gives the same lattice as the int array."""
+    nx, ny = 256, 32
+    _, obst = O.random_lattice(nx, ny, seed=3)
+    cells = O.rest_cells(nx, ny, DENSITY)
+    ref, _, _ = O.run(cells, obst, 5, DENSITY, ACCEL, OMEGA)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, obstacles=obst, flags=L.STRICT) as lat:
+        assert np.array_equal(lat.download(), cells)
+        lat.run(5)
+        a = lat.download()
+        assert lat.info().free_cells == int((obst == 0).sum())
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, obstacles=L.pack_obstacle_bits(obst), bits=True,
+                   flags=L.STRICT) as lat:
+        lat.run(5)
+        b = lat.download()
+    assert np.array_equal(a, ref)
+    assert np.array_equal(b, ref)
+
+
+def test_chunked_runs_equal_one_run():
+    """run(a); run(b) == run(a+b): no state is lost between calls (odd and even splits)."""
+    nx, ny = 128, 24
+    cells, obst = O.random_lattice(nx, ny, seed=11)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst) as lat:
+        av_all = lat.run(9)
+        one = lat.download()
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst) as lat:
+        av_parts = np.concatenate([lat.run(1), lat.run(3), lat.run(0), lat.run(5)])
+        parts = lat.download()
+    assert np.array_equal(one, parts)
+    assert np.array_equal(av_all, av_parts)
+
+
+def test_final_fields_and_av_velocity():
+    nx, ny = 128, 20
+    cells, obst = O.random_lattice(nx, ny, seed=5)
+    ref, _, _ = O.run(cells, obst, 3, DENSITY, ACCEL, OMEGA)
+    ux, uy, u, pr = O.final_state(ref, obst, DENSITY)
+    _, tot, n = O.av_velocity(ref, obst)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=L.STRICT) as lat:
+        lat.run(3)
+        gux, guy, gu, gpr = lat.final_fields()
+        assert np.array_equal(gux, ux) and np.array_equal(guy, uy)
+        assert np.array_equal(gu, u) and np.array_equal(gpr, pr)
+        # a row range
+        sub = lat.final_fields(row0=5, nrows=7)
+        assert np.array_equal(sub[3], pr[5:12])
+        assert abs(lat.av_velocity() - tot / n) <= 1e-7 * (tot / n)
+        rows = lat.download_rows(4, 3)
+        assert np.array_equal(rows, ref[4:7])
+
+
+def test_upload_round_trip():
+    nx, ny = 64, 8
+    cells, obst = O.random_lattice(nx, ny, seed=2)
+    other, _ = O.random_lattice(nx, ny, seed=99)
+    ref, _, _ = O.run(other, obst, 3, DENSITY, ACCEL, OMEGA)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=L.STRICT) as lat:
+        lat.run(1)                       # odd parity, then replace the lattice
+        lat.upload(other)
+        assert np.array_equal(lat.download(), other)
+        lat.run(3)
+        assert np.array_equal(lat.download(), ref)
+
+
+def test_f64_kernel_matches_f64_oracle():
+    nx, ny = 128, 16
+    cells, obst = O.random_lattice(nx, ny, seed=4, dtype=np.float64)
+    ref, av_ref, _ = O.run(cells, obst, 10, DENSITY, ACCEL, OMEGA)
+    for k in (L.KERNEL_SCALAR, L.KERNEL_VEC4):
+        with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, f64=True,
+                       flags=L.STRICT | k) as lat:
+            av = lat.run(10)
+            got = lat.download()
+        assert np.array_equal(got, ref)
+        np.testing.assert_allclose(av, av_ref, rtol=1e-12)
+
+
+def test_mass_is_conserved_over_many_steps():
+    """total_density (d2q9-bgk.c:2900-2916) stays constant: propagate moves, rebound swaps,
+    BGK conserves mass, accelerate_flow adds what it removes."""
+    nx, ny = 256, 128
+    _, obst = O.random_lattice(nx, ny, seed=8, p_obst=0.02)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, obstacles=obst) as lat:
+        m0 = lat.download().astype(np.float64).sum()
+        av = lat.run(2000)
+        m1 = lat.download().astype(np.float64).sum()
+    assert abs(m1 - m0) / m0 < 2e-5
+    assert np.all(np.isfinite(av)) and np.all(av > 0)
+
+
+def test_errors_are_reported_not_fatal():
+    with pytest.raises(L.LbmError, match="ny >= 2"):
+        L.Lattice(8, 1, DENSITY, ACCEL, OMEGA)
+    with pytest.raises(L.LbmError, match="nx % 4"):
+        L.Lattice(10, 4, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_VEC4)
+    with L.Lattice(8, 4, DENSITY, ACCEL, OMEGA) as lat:
+        with pytest.raises(L.LbmError, match="double precision|single precision"):
+            L.load_library().lbm_gpu_run_f64(lat.h, 1, None) and L.binding._check(1)
+        with pytest.raises(L.LbmError, match="not held"):
+            lat.download_rows(3, 5)
