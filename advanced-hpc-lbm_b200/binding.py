@@ -20,6 +20,7 @@ OBST_BITS = 2
 KERNEL_SCALAR = 4
 KERNEL_TMA = 8
 KERNEL_VEC4 = 16
+SYNC_FLAGS = 32
 IPC_DESC_BYTES = 256
 
 

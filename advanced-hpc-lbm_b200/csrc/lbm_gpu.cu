@@ -94,6 +94,7 @@ struct Slab {
   void* staging = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t step_ev[2] = {nullptr, nullptr};   // "step t finished", alternating by parity
   long long free_cells = 0;
   // neighbour views
   real* up_lattice[2] = {nullptr, nullptr};   // neighbour above (holds global row row0+rows)
@@ -119,7 +120,8 @@ class Grid : public GridBase {
   int pitch = 0, mask_pitch = 0;
   bool slab_mode = false;      // one process per GPU: neighbours are other processes
   bool connected = false;      // neighbour views are set
-  bool multi = false;          // more than one slab in the whole grid -> flag protocol
+  bool multi = false;          // more than one slab in the whole grid
+  bool use_flags = false;      // cross-slab ordering by device-side flags (else: CUDA events)
   long long global_free_cells = -1;
   long long steps_done = 0;
   long long launches = 0;
@@ -136,6 +138,8 @@ class Grid : public GridBase {
         if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
       if (s.ev0) cudaEventDestroy(s.ev0);
       if (s.ev1) cudaEventDestroy(s.ev1);
+      for (int i = 0; i < 2; i++)
+        if (s.step_ev[i]) cudaEventDestroy(s.step_ev[i]);
       if (s.stream) cudaStreamDestroy(s.stream);
       if (s.av_lo) cudaFree(s.av_lo);
       if (s.staging) cudaFree(s.staging);
@@ -166,6 +170,7 @@ class Grid : public GridBase {
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s.ev0));
     CK(cudaEventCreate(&s.ev1));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&s.step_ev[i], cudaEventDisableTiming));
     CK(cudaMemsetAsync(s.base + s.off_side[0], 0, s.bytes - s.off_side[0], s.stream));
     CK(cudaMalloc(&s.staging, kStagingBytes));
   }
@@ -277,6 +282,13 @@ class Grid : public GridBase {
       s.dn_flag = dn.sync + kFlagFromAbove;
     }
     multi = n > 1;
+    use_flags = multi && (flags & LBM_GPU_SYNC_FLAGS);
+    if (use_flags)
+      for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++)
+          if (slabs[i].device == slabs[j].device)
+            throw CudaError{"LBM_GPU_SYNC_FLAGS needs every slab on its own GPU (kernels that wait on "
+                            "one another must not share a device)"};
     connected = true;
   }
 
@@ -338,8 +350,17 @@ class Grid : public GridBase {
     for (int t = 0; t < n_steps; t++) {
       const unsigned long long step = (unsigned long long)(steps_done + t);
       const int src = (int)(step & 1), dst = src ^ 1;
-      for (auto& s : slabs) {
+      const int nslabs = (int)slabs.size();
+      for (int si = 0; si < nslabs; si++) {
+        Slab<real>& s = slabs[si];
         CK(cudaSetDevice(s.device));
+        if (multi && !use_flags && t > 0) {
+          // in-process slabs: step t needs the neighbours' step t-1 (their halo pushes
+          // into this slab, and their reads of the ghost rows this step overwrites)
+          const int up = (si + 1) % nslabs, dn = (si + nslabs - 1) % nslabs;
+          CK(cudaStreamWaitEvent(s.stream, slabs[up].step_ev[(t - 1) & 1], 0));
+          if (dn != up) CK(cudaStreamWaitEvent(s.stream, slabs[dn].step_ev[(t - 1) & 1], 0));
+        }
         lbm::StepArgs<real> a;
         a.src = s.lattice[src];
         a.dst = s.lattice[dst];
@@ -367,10 +388,11 @@ class Grid : public GridBase {
         a.aw1 = prm.density * prm.accel / (real)9;
         a.aw2 = prm.density * prm.accel / (real)36;
         const dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y));
-        if (strict) { if (multi) launch_step<true, true>(s, a, grid, block); else launch_step<true, false>(s, a, grid, block); }
-        else        { if (multi) launch_step<false, true>(s, a, grid, block); else launch_step<false, false>(s, a, grid, block); }
+        if (strict) { if (use_flags) launch_step<true, true>(s, a, grid, block); else launch_step<true, false>(s, a, grid, block); }
+        else        { if (use_flags) launch_step<false, true>(s, a, grid, block); else launch_step<false, false>(s, a, grid, block); }
         CK(cudaGetLastError());
         launches++;
+        if (multi && !use_flags) CK(cudaEventRecord(s.step_ev[t & 1], s.stream));
       }
     }
     double ms_max = 0.0;
@@ -688,7 +710,21 @@ int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_abo
     if ((dn.row0 + dn.rows) % ny != s.row0 % ny) throw CudaError{"descriptor 'below' does not hold row0-1"};
     if ((s.row0 + s.rows) % ny != up.row0 % ny) throw CudaError{"descriptor 'above' does not hold row0+nrows"};
     auto map = [&](const IpcDesc& d, int slot) -> char* {
-      if (d.pid == (int32_t)getpid() && d.base_addr == (unsigned long long)(uintptr_t)s.base) return s.base;
+      if (d.pid == (int32_t)getpid()) {
+        // exported by this very process (tests, or a host that drives several GPUs through
+        // slab handles): the address is valid here, no IPC mapping needed
+        char* p = (char*)(uintptr_t)d.base_addr;
+        if (p == s.base) return p;
+        if (d.device == s.device)
+          throw CudaError{"two slabs ordered by device-side flags must not share a GPU"};
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, s.device, d.device));
+        if (!can) throw CudaError{"peer access between the selected GPUs is not available"};
+        cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+        return p;
+      }
       void* p = nullptr;
       CK(cudaIpcOpenMemHandle(&p, d.handle, cudaIpcMemLazyEnablePeerAccess));
       s.ipc_mapped[slot] = p;
@@ -706,6 +742,7 @@ int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_abo
     s.dn_flag = (unsigned long long*)(dn_base + dn.off_sync) + kFlagFromAbove;
     s.up_flag = (unsigned long long*)(up_base + up.off_sync) + kFlagFromBelow;
     g.multi = true;
+    g.use_flags = true;      // neighbours are other processes: device-side flags
     g.connected = true;
   });
 }

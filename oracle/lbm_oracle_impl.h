@@ -117,22 +117,35 @@ static inline REAL NAME(cell_speed)(const REAL* f, REAL* ux_out, REAL* uy_out, R
   return SQRT((u_x * u_x) + (u_y * u_y));
 }
 
-/* ---- rebound: d2q9-bgk.c:2199-2228.  Reads the propagated grid `tmp_cells`,
- * writes the bounced values into `cells` for obstacle cells only. ------------- */
-void NAME(oracle_rebound)(int nx, int ny, REAL* cells, const REAL* tmp_cells, const int* obstacles)
+/* ---- rebound: d2q9-bgk.c:2199-2228.  Called after propagate: swaps the opposite
+ * directions of obstacle cells IN PLACE in the propagated grid `tmp_cells` (the
+ * reference's `cells` argument is unused there too). --------------------------- */
+void NAME(oracle_rebound)(int nx, int ny, REAL* cells, REAL* tmp_cells, const int* obstacles)
 {
+  (void)cells;
   for (size_t n = 0; n < (size_t)nx * ny; n++)
-    if (obstacles[n]) NAME(cell_rebound)(tmp_cells + n * 9, cells + n * 9);
+    if (obstacles[n]) {
+      REAL p[9], o[9];
+      for (int k = 0; k < 9; k++) p[k] = tmp_cells[n * 9 + k];
+      NAME(cell_rebound)(p, o);
+      for (int k = 0; k < 9; k++) tmp_cells[n * 9 + k] = o[k];
+    }
 }
 
-/* ---- collision: d2q9-bgk.c:2554-2663.  Reads the propagated grid `tmp_cells`,
- * writes relaxed values into `cells` for fluid cells only. -------------------- */
-void NAME(oracle_collision)(int nx, int ny, REAL omega, REAL* cells, const REAL* tmp_cells,
+/* ---- collision: d2q9-bgk.c:2554-2663.  Called after propagate/rebound: relaxes the
+ * fluid cells IN PLACE in `tmp_cells` (:2646-2651). --------------------------- */
+void NAME(oracle_collision)(int nx, int ny, REAL omega, REAL* cells, REAL* tmp_cells,
                             const int* obstacles)
 {
+  (void)cells;
 #pragma omp parallel for schedule(static)
   for (long n = 0; n < (long)nx * ny; n++)
-    if (!obstacles[n]) NAME(cell_collide)(tmp_cells + (size_t)n * 9, omega, cells + (size_t)n * 9);
+    if (!obstacles[n]) {
+      REAL p[9], o[9];
+      for (int k = 0; k < 9; k++) p[k] = tmp_cells[(size_t)n * 9 + k];
+      NAME(cell_collide)(p, omega, o);
+      for (int k = 0; k < 9; k++) tmp_cells[(size_t)n * 9 + k] = o[k];
+    }
 }
 
 /* ---- av_velocity: d2q9-bgk.c:2665-2714.  Serial REAL accumulator in row-major
@@ -218,9 +231,9 @@ REAL NAME(oracle_timestep)(int nx, int ny, REAL density, REAL accel, REAL omega,
   return tot_u / (REAL)tot_cells;                         /* :1811 */
 }
 
-/* ---- the un-fused semantic step: timestep_old order, d2q9-bgk.c:1824-1831 plus
- * av_velocity on the result (main's commented line :193).  Same result grid as
- * the fused step but delivered into `cells` (tmp_cells is scratch). ----------- */
+/* ---- the un-fused semantic step: timestep_old order, d2q9-bgk.c:1824-1831, with
+ * av_velocity taken on the grid that holds the result (`tmp_cells`, which main swaps
+ * into `cells` at :190).  Same result grid as the fused step. ------------------ */
 REAL NAME(oracle_timestep_unfused)(int nx, int ny, REAL density, REAL accel, REAL omega,
                                    REAL* cells, REAL* tmp_cells, const int* obstacles)
 {
@@ -228,7 +241,7 @@ REAL NAME(oracle_timestep_unfused)(int nx, int ny, REAL density, REAL accel, REA
   NAME(oracle_propagate)(nx, ny, cells, tmp_cells);
   NAME(oracle_rebound)(nx, ny, cells, tmp_cells, obstacles);
   NAME(oracle_collision)(nx, ny, omega, cells, tmp_cells, obstacles);
-  return NAME(oracle_av_velocity)(nx, ny, cells, obstacles, 0, 0);
+  return NAME(oracle_av_velocity)(nx, ny, tmp_cells, obstacles, 0, 0);
 }
 
 /* ---- rest-state initialisation: d2q9-bgk.c:2802-2823 ------------------------- */

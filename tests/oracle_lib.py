@@ -87,7 +87,7 @@ def timestep_unfused(cells, obstacles, density, accel, omega):
     fn.argtypes = [C.c_int, C.c_int, ct, ct, ct, C.c_void_p, C.c_void_p, C.c_void_p]
     fn.restype = ct
     av = fn(nx, ny, density, accel, omega, _p(a), _p(b), _p(obst))
-    return a, av
+    return b, av
 
 
 def final_state(cells, obstacles, density):

@@ -1,0 +1,135 @@
+"""Row-slab decomposition on the GPU: N slabs must give the SAME BITS as one slab --
+lattice, av_vels and final fields -- because every cell sees the same inputs and the
+per-step |u| sum is an exact integer accumulation.
+
+  * several slabs on ONE device, ordered by CUDA events: runs on a single-GPU box and
+    exercises ghost rows, halo pushes, the owner of the accelerated row ny-2 and uneven
+    / one-row slabs;
+  * real multi-GPU (needs >= 2 devices): event ordering, the device-side flag protocol,
+    and the one-process-per-GPU form over CUDA IPC under torch.distributed.run.
+"""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import lbm_b200 as L
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+D, A, W = 0.1, 0.005, 1.85
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ndev():
+    return L.load_library().lbm_gpu_device_count()
+
+
+def single(nx, ny, cells, obst, steps, flags=0):
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=flags) as lat:
+        av = lat.run(steps)
+        return lat.download(), av, lat.final_fields()
+
+
+@pytest.mark.parametrize("nx,ny,n", [(128, 64, 2), (128, 64, 4), (64, 10, 3), (64, 7, 7), (32, 3, 2),
+                                     (36, 5, 4), (37, 9, 2), (256, 33, 8)])
+def test_slabs_on_one_device_equal_single_slab(nx, ny, n):
+    steps = 12
+    cells, obst = O.random_lattice(nx, ny, seed=nx + ny + n)
+    ref, av_ref, fields_ref = single(nx, ny, cells, obst, steps)
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, n_gpus=n, device_ids=[0] * n) as lat:
+        av = np.concatenate([lat.run(5), lat.run(steps - 5)])
+        got = lat.download()
+        fields = lat.final_fields()
+        assert lat.info().n_gpus == n
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(av, av_ref)
+    for a, b in zip(fields, fields_ref):
+        assert np.array_equal(a, b)
+
+
+def test_slabs_strict_equal_oracle():
+    nx, ny, n, steps = 64, 11, 3, 6
+    cells, obst = O.random_lattice(nx, ny, seed=5)
+    ref, _, _ = O.run(cells, obst, steps, D, A, W)
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, n_gpus=n, device_ids=[0] * n,
+                   flags=L.STRICT) as lat:
+        lat.run(steps)
+        assert np.array_equal(lat.download(), ref)
+
+
+def test_flag_protocol_refuses_a_shared_device():
+    with pytest.raises(L.LbmError, match="own GPU"):
+        L.Lattice(64, 8, D, A, W, n_gpus=2, device_ids=[0, 0], flags=L.SYNC_FLAGS)
+
+
+@pytest.mark.parametrize("mode", ["events", "flags"])
+def test_real_multi_gpu_equals_single(mode):
+    n = min(ndev(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nx, ny, steps = 512, 203, 40
+    cells, obst = O.random_lattice(nx, ny, seed=1, p_obst=0.02)
+    ref, av_ref, _ = single(nx, ny, cells, obst, steps)
+    flags = L.SYNC_FLAGS if mode == "flags" else 0
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, n_gpus=n, flags=flags) as lat:
+        av = lat.run(steps)
+        got = lat.download()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(av, av_ref)
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+    import torch, torch.distributed as dist
+    import lbm_b200 as L
+    import oracle_lib as O
+    from importlib import import_module
+    slabs = import_module("advanced-hpc-lbm_b200.slabs")
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny, steps = %(nx)d, %(ny)d, %(steps)d
+    cells, obst = O.random_lattice(nx, ny, seed=1, p_obst=0.02)
+    r0, k = L.split_rows(ny, world)[rank]
+    lat = L.Lattice(nx, ny, 0.1, 0.005, 1.85, cells=cells[r0:r0 + k], obstacles=obst[r0:r0 + k],
+                    slab=(r0, k), device_ids=[local])
+    below, above = slabs.exchange_descriptors(lat.ipc_export(), rank, world, dist)
+    lat.ipc_connect(below, above)
+    dist.barrier(); lat.ipc_prepare(); dist.barrier()
+    sums = np.concatenate([lat.run_sums(7), lat.run_sums(steps - 7)])
+    av = slabs.combine_step_sums(sums, lat.info().local_free_cells, dist, world)
+    np.save(os.path.join(%(out)r, "rows_%%d.npy" %% rank), lat.download())
+    if rank == 0:
+        np.save(os.path.join(%(out)r, "av.npy"), av)
+    dist.barrier()
+    lat.close()
+    dist.destroy_process_group()
+""")
+
+
+def test_one_process_per_gpu_over_ipc_equals_single(tmp_path):
+    n = min(ndev(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nx, ny, steps = 512, 203, 40
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "nx": nx, "ny": ny, "steps": steps, "out": str(tmp_path)})
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n,
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:]
+    cells, obst = O.random_lattice(nx, ny, seed=1, p_obst=0.02)
+    ref, av_ref, _ = single(nx, ny, cells, obst, steps)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), "rows_%d.npy" % i)) for i in range(n)])
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    av = np.load(os.path.join(str(tmp_path), "av.npy"))
+    # the sums are exact integers on the device; only the final double division differs
+    np.testing.assert_allclose(av, av_ref.astype(np.float64), rtol=2e-7)

@@ -39,24 +39,30 @@ def shipped_mask(name):
     return m
 
 
-def channel_mask(nx, ny, p=0.01, seed=20240229, block_accel_row=False):
+CHUNK_ROWS = 1024
+
+
+def channel_mask(nx, ny, p=0.01, seed=20240229, block_accel_row=False, rows=None):
     """Walls at rows 0 and ny-1, Bernoulli(p) obstacles elsewhere.
 
     Row ny-2 (the accelerated row, d2q9-bgk.c:240) is kept free unless
     block_accel_row, in which case it takes the random obstacles like any other row.
-    Generated row by row so that a grid of the same seed and nx but smaller ny is a
-    prefix of the larger one apart from the top wall (useful for reduced-height
-    replicas of the weak-scaling grids)."""
-    m = np.zeros((ny, nx), dtype=np.uint8)
-    rng = np.random.default_rng(seed)
-    chunk = 1024
-    for y0 in range(0, ny, chunk):
-        y1 = min(ny, y0 + chunk)
-        m[y0:y1] = rng.random((y1 - y0, nx), dtype=np.float32) < p
-    m[0, :] = 1
-    m[ny - 1, :] = 1
-    if not block_accel_row:
-        m[ny - 2, :] = 0
+    Every block of 1024 rows has its own random stream seeded by (seed, block index), so
+    a rank can generate just its rows (`rows=(r0, r1)`) and a grid of the same seed and
+    nx but smaller ny equals the larger one apart from its last two rows (used for
+    reduced-height CPU replicas of the weak-scaling grids)."""
+    r0, r1 = (0, ny) if rows is None else rows
+    m = np.zeros((r1 - r0, nx), dtype=np.uint8)
+    for c in range(r0 // CHUNK_ROWS, (r1 + CHUNK_ROWS - 1) // CHUNK_ROWS):
+        rng = np.random.default_rng([seed, c])
+        block = rng.random((CHUNK_ROWS, nx), dtype=np.float32) < p
+        a, b = max(r0, c * CHUNK_ROWS), min(r1, (c + 1) * CHUNK_ROWS)
+        m[a - r0:b - r0] = block[a - c * CHUNK_ROWS:b - c * CHUNK_ROWS]
+    for wall in (0, ny - 1):
+        if r0 <= wall < r1:
+            m[wall - r0, :] = 1
+    if not block_accel_row and r0 <= ny - 2 < r1:
+        m[ny - 2 - r0, :] = 0
     return m
 
 
