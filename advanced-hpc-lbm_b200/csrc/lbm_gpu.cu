@@ -58,12 +58,11 @@ struct IpcDesc {
   int32_t nx, pitch, rows;
   int32_t pad_;
   long long row0;
-  long long plane_stride;
-  unsigned long long base_addr;       // only meaningful inside the exporting process
-  unsigned long long off_lattice[2];  // byte offsets inside the allocation
-  unsigned long long off_sync;
+  unsigned long long win_addr;        // only meaningful inside the exporting process
+  unsigned long long win_bytes;
+  unsigned long long off_sync;        // byte offset of the sync words inside the window
   unsigned long long steps_done;
-  cudaIpcMemHandle_t handle;
+  cudaIpcMemHandle_t handle;          // of the halo window (the lattice itself is never shared)
 };
 static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large");
 constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
@@ -81,13 +80,17 @@ struct Slab {
   int device = 0;
   long long row0 = 0;   // first global row
   int rows = 0;         // local rows
-  int accel_row = -1;   // local row (1-based) of global row ny-2, or -1
-  char* base = nullptr; // the one allocation: lattice[2] | side[2] | mask | sync words
+  int accel_row = LBM_NO_ROW;   // local row of global row ny-2, or LBM_NO_ROW
+  char* base = nullptr; // lattice[2] | side[2] | mask (private to this GPU)
   size_t bytes = 0;
-  size_t off_lattice[2] = {0, 0}, off_side[2] = {0, 0}, off_mask = 0, off_sync = 0;
+  size_t off_lattice[2] = {0, 0}, off_side[2] = {0, 0}, off_mask = 0;
   real* lattice[2] = {nullptr, nullptr};
   real* side[2] = {nullptr, nullptr};
   uint32_t* mask = nullptr;
+  // halo window: [parity 2][direction 2][3 planes][pitch] reals, then the sync words.
+  // The only memory neighbours (other GPUs / processes) read or write.
+  char* win = nullptr;
+  size_t win_bytes = 0, off_sync = 0;
   unsigned long long* sync = nullptr;
   unsigned long long *av_lo = nullptr, *av_hi = nullptr;
   size_t av_cap = 0;
@@ -96,11 +99,9 @@ struct Slab {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t step_ev[2] = {nullptr, nullptr};   // "step t finished", alternating by parity
   long long free_cells = 0;
-  // neighbour views
-  real* up_lattice[2] = {nullptr, nullptr};   // neighbour above (holds global row row0+rows)
-  real* dn_lattice[2] = {nullptr, nullptr};   // neighbour below (holds global row row0-1)
-  long long up_plane_stride = 0, dn_plane_stride = 0;
-  int dn_rows = 0;
+  // neighbour views: the windows of the slab above (holds global row row0+rows) and below
+  char* up_win = nullptr;
+  char* dn_win = nullptr;
   unsigned long long* up_flag = nullptr;      // neighbour above's kFlagFromBelow
   unsigned long long* dn_flag = nullptr;      // neighbour below's kFlagFromAbove
   void* ipc_mapped[2] = {nullptr, nullptr};   // pointers to close on destroy
@@ -143,6 +144,7 @@ class Grid : public GridBase {
       if (s.stream) cudaStreamDestroy(s.stream);
       if (s.av_lo) cudaFree(s.av_lo);
       if (s.staging) cudaFree(s.staging);
+      if (s.win) cudaFree(s.win);
       if (s.base) cudaFree(s.base);
     }
   }
@@ -150,7 +152,7 @@ class Grid : public GridBase {
   // ---------------------------------------------------------------- allocation ----
   void alloc_slab(Slab<real>& s) {
     CK(cudaSetDevice(s.device));
-    const long long plane = (long long)(s.rows + 2) * pitch;
+    const long long plane = (long long)s.rows * pitch;
     const size_t lat = (size_t)9 * plane * sizeof(real);
     const size_t side = (size_t)6 * pitch * sizeof(real);
     const size_t maskb = (size_t)s.rows * mask_pitch * sizeof(uint32_t);
@@ -158,7 +160,6 @@ class Grid : public GridBase {
     for (int i = 0; i < 2; i++) { s.off_lattice[i] = off; off = round_up(off + lat, 256); }
     for (int i = 0; i < 2; i++) { s.off_side[i] = off; off = round_up(off + side, 256); }
     s.off_mask = off; off = round_up(off + maskb, 256);
-    s.off_sync = off; off = round_up(off + kSyncWords * sizeof(unsigned long long), 256);
     s.bytes = off;
     CK(cudaMalloc((void**)&s.base, s.bytes));
     for (int i = 0; i < 2; i++) {
@@ -166,16 +167,25 @@ class Grid : public GridBase {
       s.side[i] = (real*)(s.base + s.off_side[i]);
     }
     s.mask = (uint32_t*)(s.base + s.off_mask);
-    s.sync = (unsigned long long*)(s.base + s.off_sync);
+    // the window gets its own allocation, a multiple of 2 MiB so that it never shares a
+    // driver block with anything else (it is exported over CUDA IPC)
+    s.off_sync = round_up((size_t)12 * pitch * sizeof(real), 256);
+    s.win_bytes = round_up(s.off_sync + kSyncWords * sizeof(unsigned long long), 2u << 20);
+    CK(cudaMalloc((void**)&s.win, s.win_bytes));
+    s.sync = (unsigned long long*)(s.win + s.off_sync);
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s.ev0));
     CK(cudaEventCreate(&s.ev1));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&s.step_ev[i], cudaEventDisableTiming));
     CK(cudaMemsetAsync(s.base + s.off_side[0], 0, s.bytes - s.off_side[0], s.stream));
+    CK(cudaMemsetAsync(s.win, 0, s.win_bytes, s.stream));
     CK(cudaMalloc(&s.staging, kStagingBytes));
   }
 
-  long long plane_stride(const Slab<real>& s) const { return (long long)(s.rows + 2) * pitch; }
+  // window section: parity b, direction d (0 = "from below": speeds 2,5,6; 1 = "from above": 4,7,8)
+  real* win_section(char* win, int b, int d) const { return (real*)win + (size_t)((b * 2 + d) * 3) * pitch; }
+
+  long long plane_stride(const Slab<real>& s) const { return (long long)s.rows * pitch; }
 
   void setup_geometry(int nx) {
     pitch = (int)round_up(nx, 32);
@@ -248,7 +258,7 @@ class Grid : public GridBase {
       CK(cudaMemcpyAsync(s.staging, (const char*)cells_aos + (size_t)r * row_bytes, (size_t)n * row_bytes,
                          cudaMemcpyHostToDevice, s.stream));
       lbm::lbm_aos_to_soa<real><<<(unsigned)((ncells * 9 + 255) / 256), 256, 0, s.stream>>>(
-          (const real*)s.staging, s.lattice[cur], plane_stride(s), pitch, nx, r + 1, ncells);
+          (const real*)s.staging, s.lattice[cur], plane_stride(s), pitch, nx, r, ncells);
       CK(cudaGetLastError());
       launches++;
       CK(cudaStreamSynchronize(s.stream));
@@ -274,10 +284,8 @@ class Grid : public GridBase {
           cudaGetLastError();
         }
       }
-      for (int b = 0; b < 2; b++) { s.up_lattice[b] = up.lattice[b]; s.dn_lattice[b] = dn.lattice[b]; }
-      s.up_plane_stride = plane_stride(up);
-      s.dn_plane_stride = plane_stride(dn);
-      s.dn_rows = dn.rows;
+      s.up_win = up.win;
+      s.dn_win = dn.win;
       s.up_flag = up.sync + kFlagFromBelow;
       s.dn_flag = dn.sync + kFlagFromAbove;
     }
@@ -301,10 +309,8 @@ class Grid : public GridBase {
       a.cur = s.lattice[cur];
       a.side_cur = s.side[cur];
       a.mask = s.mask;
-      a.up_ghost = s.up_lattice[cur];
-      a.dn_ghost = s.dn_lattice[cur] + (long long)(s.dn_rows + 1) * pitch;
-      a.up_plane_stride = s.up_plane_stride;
-      a.dn_plane_stride = s.dn_plane_stride;
+      a.push_up = win_section(s.up_win, cur, 0);
+      a.push_dn = win_section(s.dn_win, cur, 1);
       a.plane_stride = plane_stride(s);
       a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch; a.accel_row = s.accel_row;
       a.aw1 = prm.density * prm.accel / (real)9;      // d2q9-bgk.c:230-231
@@ -369,10 +375,10 @@ class Grid : public GridBase {
         a.mask = s.mask;
         a.av_lo = s.av_lo + t;
         a.av_hi = s.av_hi + t;
-        a.up_ghost = s.up_lattice[dst];
-        a.dn_ghost = s.dn_lattice[dst] + (long long)(s.dn_rows + 1) * pitch;
-        a.up_plane_stride = s.up_plane_stride;
-        a.dn_plane_stride = s.dn_plane_stride;
+        a.halo_s = win_section(s.win, src, 0);
+        a.halo_n = win_section(s.win, src, 1);
+        a.push_up = win_section(s.up_win, dst, 0);
+        a.push_dn = win_section(s.dn_win, dst, 1);
         a.flag_from_below = s.sync + kFlagFromBelow;
         a.flag_from_above = s.sync + kFlagFromAbove;
         a.up_flag = s.up_flag;
@@ -448,7 +454,7 @@ class Grid : public GridBase {
       const int n = (int)std::min<long long>({(long long)chunk_rows, s.row0 + s.rows - g, row0 + nrows - g});
       const long long ncells = (long long)n * nx;
       lbm::lbm_soa_to_aos<real><<<(unsigned)((ncells * 9 + 255) / 256), 256, 0, s.stream>>>(
-          s.lattice[cur], (real*)s.staging, plane_stride(s), pitch, nx, (int)(g - s.row0) + 1, ncells);
+          s.lattice[cur], (real*)s.staging, plane_stride(s), pitch, nx, (int)(g - s.row0), ncells);
       CK(cudaGetLastError());
       launches++;
       CK(cudaMemcpyAsync((char*)out + (size_t)(g - row0) * row_bytes, s.staging, (size_t)n * row_bytes,
@@ -475,7 +481,7 @@ class Grid : public GridBase {
       real* d_u = u ? st + 2 * ncells : nullptr;
       real* d_p = p ? st + 3 * ncells : nullptr;
       lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
-          s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, nx, (int)(g - s.row0) + 1, n,
+          s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, nx, (int)(g - s.row0), n,
           prm.density, d_ux, d_uy, d_u, d_p, nullptr, nullptr);
       CK(cudaGetLastError());
       launches++;
@@ -499,7 +505,7 @@ class Grid : public GridBase {
       CK(cudaMemsetAsync(lo, 0, 2 * sizeof(unsigned long long), s.stream));
       const long long ncells = (long long)s.rows * prm.nx;
       lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
-          s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, prm.nx, 1, s.rows, prm.density,
+          s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, prm.nx, 0, s.rows, prm.density,
           nullptr, nullptr, nullptr, nullptr, lo, hi);
       CK(cudaGetLastError());
       launches++;
@@ -556,7 +562,7 @@ int create_impl(const typename ParamT<real>::type* params, const real* cells_aos
       s.row0 = row0[i];
       s.rows = rows[i];
       const long long ar = (long long)params->ny - 2;
-      s.accel_row = (ar >= s.row0 && ar < s.row0 + s.rows) ? (int)(ar - s.row0) + 1 : -1;
+      s.accel_row = (ar >= s.row0 && ar < s.row0 + s.rows) ? (int)(ar - s.row0) : LBM_NO_ROW;
       g->alloc_slab(s);
       g->load_slab(s, cells_aos ? cells_aos + (size_t)s.row0 * cell_row : nullptr,
                    obstacles ? (const char*)obstacles + (size_t)s.row0 * obst_row_bytes : nullptr, 0);
@@ -656,7 +662,7 @@ int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows
     s.row0 = row0;
     s.rows = (int)nrows;
     const long long ar = (long long)params->ny - 2;
-    s.accel_row = (ar >= row0 && ar < row0 + nrows) ? (int)(ar - row0) + 1 : -1;
+    s.accel_row = (ar >= row0 && ar < row0 + nrows) ? (int)(ar - row0) : LBM_NO_ROW;
     g->alloc_slab(s);
     g->load_slab(s, cells_aos_rows, obstacles_rows, 0);
     if (nrows == params->ny) { g->connect_local(); g->prepare(); }   // whole grid in one slab
@@ -681,12 +687,11 @@ int lbm_gpu_ipc_export(lbm_gpu* h, void* desc) {
     d.pid = (int32_t)getpid();
     d.nx = g.prm.nx; d.pitch = g.pitch; d.rows = s.rows;
     d.row0 = s.row0;
-    d.plane_stride = g.plane_stride(s);
-    d.base_addr = (unsigned long long)(uintptr_t)s.base;
-    d.off_lattice[0] = s.off_lattice[0]; d.off_lattice[1] = s.off_lattice[1];
+    d.win_addr = (unsigned long long)(uintptr_t)s.win;
+    d.win_bytes = s.win_bytes;
     d.off_sync = s.off_sync;
     d.steps_done = (unsigned long long)g.steps_done;
-    CK(cudaIpcGetMemHandle(&d.handle, s.base));
+    CK(cudaIpcGetMemHandle(&d.handle, s.win));
     memset(desc, 0, LBM_GPU_IPC_DESC_BYTES);
     memcpy(desc, &d, sizeof d);
   });
@@ -713,8 +718,8 @@ int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_abo
       if (d.pid == (int32_t)getpid()) {
         // exported by this very process (tests, or a host that drives several GPUs through
         // slab handles): the address is valid here, no IPC mapping needed
-        char* p = (char*)(uintptr_t)d.base_addr;
-        if (p == s.base) return p;
+        char* p = (char*)(uintptr_t)d.win_addr;
+        if (p == s.win) return p;
         if (d.device == s.device)
           throw CudaError{"two slabs ordered by device-side flags must not share a GPU"};
         int can = 0;
@@ -730,17 +735,12 @@ int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_abo
       s.ipc_mapped[slot] = p;
       return (char*)p;
     };
-    char* dn_base = map(dn, 0);
-    char* up_base = (memcmp(&dn.handle, &up.handle, sizeof dn.handle) == 0 && dn.pid == up.pid) ? dn_base : map(up, 1);
-    for (int b = 0; b < 2; b++) {
-      s.dn_lattice[b] = (float*)(dn_base + dn.off_lattice[b]);
-      s.up_lattice[b] = (float*)(up_base + up.off_lattice[b]);
-    }
-    s.dn_plane_stride = dn.plane_stride;
-    s.up_plane_stride = up.plane_stride;
-    s.dn_rows = dn.rows;
-    s.dn_flag = (unsigned long long*)(dn_base + dn.off_sync) + kFlagFromAbove;
-    s.up_flag = (unsigned long long*)(up_base + up.off_sync) + kFlagFromBelow;
+    for (const IpcDesc* d : {&dn, &up})
+      if (d->win_bytes != s.win_bytes || d->off_sync != s.off_sync) throw CudaError{"neighbour window layout differs"};
+    s.dn_win = map(dn, 0);
+    s.up_win = (memcmp(&dn.handle, &up.handle, sizeof dn.handle) == 0 && dn.pid == up.pid) ? s.dn_win : map(up, 1);
+    s.dn_flag = (unsigned long long*)(s.dn_win + dn.off_sync) + kFlagFromAbove;
+    s.up_flag = (unsigned long long*)(s.up_win + up.off_sync) + kFlagFromBelow;
     g.multi = true;
     g.use_flags = true;      // neighbours are other processes: device-side flags
     g.connected = true;

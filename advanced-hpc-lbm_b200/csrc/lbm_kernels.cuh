@@ -6,9 +6,13 @@
 // (:1103-1130), plus -- new here -- the halo push into the neighbouring slabs.
 //
 // Data layout in HBM (one "slab" = the rows one GPU holds):
-//   lattice  2 buffers x 9 planes x (rows+2) x pitch   structure-of-arrays; local row 0
-//            and rows+1 are ghost rows holding the neighbours' edge rows (periodic in y,
-//            so with one slab they hold the slab's own opposite edge);
+//   lattice  2 buffers x 9 planes x rows x pitch   structure-of-arrays;
+//   window   2 parities x 2 directions x 3 planes x pitch: the halo rows.  "from below"
+//            holds speeds 2,5,6 of the row under the slab's first row, "from above"
+//            speeds 4,7,8 of the row over its last row (periodic in y, so with one slab
+//            they are the slab's own opposite edge rows).  Written by the NEIGHBOURS'
+//            step kernels (peer stores over NVLink), read by this slab's edge rows.  It
+//            is the only memory other GPUs / processes map, together with the flags;
 //   mask     rows x pitch/32 uint32, bit = 1 for an obstacle cell;
 //   side     2 x 6 x pitch: row ny-2 of planes 1,3,5,6,7,8 AFTER accelerate_flow.
 //            The lattice itself always holds the un-accelerated state; readers that
@@ -204,11 +208,11 @@ struct StepArgs {
   const uint32_t* mask;        // rows x mask_pitch words
   unsigned long long* av_lo;   // this step's 128-bit |u| sum, low / high word
   unsigned long long* av_hi;
-  // halo push targets: ghost rows of the neighbours' dst buffers (plane 0 of that row)
-  real* up_ghost;              // neighbour above: its local row 0
-  real* dn_ghost;              // neighbour below: its local row rows'+1
-  long long up_plane_stride;   // plane strides of the neighbours' lattices
-  long long dn_plane_stride;
+  // halo rows: 3 x pitch each, see "window" above
+  const real* halo_s;          // own window, src parity: speeds {2,5,6} of the row below row 0
+  const real* halo_n;          // own window, src parity: speeds {4,7,8} of the row above row rows-1
+  real* push_up;               // neighbour above's window, dst parity, "from below": {2,5,6}
+  real* push_dn;               // neighbour below's window, dst parity, "from above": {4,7,8}
   // cross-slab ordering (only when MULTI)
   volatile unsigned long long* flag_from_below;  // local: steps completed by neighbour below
   volatile unsigned long long* flag_from_above;
@@ -216,16 +220,18 @@ struct StepArgs {
   unsigned long long* dn_flag;                   // neighbour below's flag_from_above
   unsigned long long* boundary_done;             // local counter of finished boundary blocks
   unsigned long long step;                       // global index of this step (0-based)
-  long long plane_stride;      // (rows+2) * pitch
+  long long plane_stride;      // rows * pitch
   int nx;
-  int rows;                    // local rows (R)
+  int rows;                    // local rows
   int pitch;                   // elements per row, multiple of 32
   int mask_pitch;              // words per mask row
-  int accel_row;               // local row (1-based) holding global row ny-2, or -1
+  int accel_row;               // local row holding global row ny-2, or LBM_NO_ROW
   int tiles_x, tiles_y;
   real omega;
   real aw1, aw2;               // density*accel/9, density*accel/36 (d2q9-bgk.c:230-231)
 };
+
+#define LBM_NO_ROW (-1000)
 
 template <typename real> struct alignas(4 * sizeof(real)) Vec4 { real x, y, z, w; };
 
@@ -320,30 +326,33 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   boundary_wait<real, MULTI>(a, is_boundary);
 
   const int x0 = (tx * (int)blockDim.x + (int)threadIdx.x) * 4;
-  const int r = 1 + ty * (int)blockDim.y + (int)threadIdx.y;    // local row, 1-based
-  const bool active = (x0 < a.nx) && (r <= a.rows);
+  const int r = ty * (int)blockDim.y + (int)threadIdx.y;        // local row
+  const bool active = (x0 < a.nx) && (r < a.rows);
   const int lane = threadIdx.x & 31;
   unsigned long long q = 0ULL;
 
   // clamp so that inactive threads still form valid addresses (they take part in the
   // shuffles but never store)
   const int xc = active ? x0 : 0;
-  const int rc = active ? r : 1;
+  const int rc = active ? r : 0;
   const long long PS = a.plane_stride;
   const long long oC = (long long)rc * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
 
-  // planes 1,3 of the centre row / 5,6 of the south row / 7,8 of the north row come
-  // from the accelerated side row when that row is global row ny-2
+  // Row sources.  South/north neighbours of the slab's first/last row live in the halo
+  // window; planes 1,3 of the centre row / 5,6 of the south row / 7,8 of the north row
+  // come from the accelerated side row when that row is global row ny-2 (the window
+  // already holds accelerated values).  All of this is warp-uniform.
+  const bool first = (rc == 0), last = (rc == a.rows - 1);
   const bool cA = (rc == a.accel_row), sA = (rc - 1 == a.accel_row), nA = (rc + 1 == a.accel_row);
   const real* p0 = a.src + oC;
   const real* p1 = cA ? a.side_src + 0 * a.pitch : a.src + 1 * PS + oC;
-  const real* p2 = a.src + 2 * PS + oS;
   const real* p3 = cA ? a.side_src + 1 * a.pitch : a.src + 3 * PS + oC;
-  const real* p4 = a.src + 4 * PS + oN;
-  const real* p5 = sA ? a.side_src + 2 * a.pitch : a.src + 5 * PS + oS;
-  const real* p6 = sA ? a.side_src + 3 * a.pitch : a.src + 6 * PS + oS;
-  const real* p7 = nA ? a.side_src + 4 * a.pitch : a.src + 7 * PS + oN;
-  const real* p8 = nA ? a.side_src + 5 * a.pitch : a.src + 8 * PS + oN;
+  const real* p2 = first ? a.halo_s + 0 * a.pitch : a.src + 2 * PS + oS;
+  const real* p5 = first ? a.halo_s + 1 * a.pitch : (sA ? a.side_src + 2 * a.pitch : a.src + 5 * PS + oS);
+  const real* p6 = first ? a.halo_s + 2 * a.pitch : (sA ? a.side_src + 3 * a.pitch : a.src + 6 * PS + oS);
+  const real* p4 = last ? a.halo_n + 0 * a.pitch : a.src + 4 * PS + oN;
+  const real* p7 = last ? a.halo_n + 1 * a.pitch : (nA ? a.side_src + 4 * a.pitch : a.src + 7 * PS + oN);
+  const real* p8 = last ? a.halo_n + 2 * a.pitch : (nA ? a.side_src + 5 * a.pitch : a.src + 8 * PS + oN);
 
   // edge elements first (scalar, predicated), then the nine aligned vectors
   const bool need_w = (lane == 0) || (xc == 0);
@@ -357,7 +366,7 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   const Vec4<real> v0 = ld4(p0 + xc), v1 = ld4(p1 + xc), v2 = ld4(p2 + xc), v3 = ld4(p3 + xc),
                    v4 = ld4(p4 + xc), v5 = ld4(p5 + xc), v6 = ld4(p6 + xc), v7 = ld4(p7 + xc),
                    v8 = ld4(p8 + xc);
-  const uint32_t mword = a.mask[(long long)(rc - 1) * a.mask_pitch + (xc >> 5)];
+  const uint32_t mword = a.mask[(long long)rc * a.mask_pitch + (xc >> 5)];
   const uint32_t mbits = (mword >> (xc & 31)) & 0xFu;
 
   // element x0-1 of planes 1,5,8 and x0+4 of planes 3,6,7 from the neighbouring lanes
@@ -392,9 +401,8 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
       Vec4<real> v; v.x = out[0][k]; v.y = out[1][k]; v.z = out[2][k]; v.w = out[3][k];
       st4(d + k * PS, v);
     }
-    const bool first = (r == 1), last = (r == a.rows), acc = (r == a.accel_row);
-    if (first | last | acc) {         // warp-uniform: a warp never spans two rows
-      if (acc) {
+    if (first | last | cA) {          // warp-uniform: a warp never spans two rows
+      if (cA) {
         // next step's accelerate_flow on the row just produced (d2q9-bgk.c:229-260)
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -412,7 +420,7 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
-          st4(a.dn_ghost + ks[i] * a.dn_plane_stride + xc, v);
+          st4(a.push_dn + (long long)i * a.pitch + xc, v);
         }
       }
       if (last) {                     // speeds 2,5,6 are pulled by the row above
@@ -420,7 +428,7 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
-          st4(a.up_ghost + ks[i] * a.up_plane_stride + xc, v);
+          st4(a.push_up + (long long)i * a.pitch + xc, v);
         }
       }
     }
@@ -444,45 +452,46 @@ lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
   boundary_wait<real, MULTI>(a, is_boundary);
 
   const int x = tx * (int)blockDim.x + (int)threadIdx.x;
-  const int r = 1 + ty * (int)blockDim.y + (int)threadIdx.y;
-  const bool active = (x < a.nx) && (r <= a.rows);
+  const int r = ty * (int)blockDim.y + (int)threadIdx.y;
+  const bool active = (x < a.nx) && (r < a.rows);
   unsigned long long q = 0ULL;
   if (active) {
     const long long PS = a.plane_stride;
     const long long oC = (long long)r * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
+    const bool first = (r == 0), last = (r == a.rows - 1);
     const bool cA = (r == a.accel_row), sA = (r - 1 == a.accel_row), nA = (r + 1 == a.accel_row);
     const int xw = (x == 0) ? a.nx - 1 : x - 1;
     const int xe = (x + 1 == a.nx) ? 0 : x + 1;
     real p[9], o[9];
     p[0] = a.src[oC + x];
     p[1] = cA ? a.side_src[0 * a.pitch + xw] : a.src[1 * PS + oC + xw];
-    p[2] = a.src[2 * PS + oS + x];
     p[3] = cA ? a.side_src[1 * a.pitch + xe] : a.src[3 * PS + oC + xe];
-    p[4] = a.src[4 * PS + oN + x];
-    p[5] = sA ? a.side_src[2 * a.pitch + xw] : a.src[5 * PS + oS + xw];
-    p[6] = sA ? a.side_src[3 * a.pitch + xe] : a.src[6 * PS + oS + xe];
-    p[7] = nA ? a.side_src[4 * a.pitch + xe] : a.src[7 * PS + oN + xe];
-    p[8] = nA ? a.side_src[5 * a.pitch + xw] : a.src[8 * PS + oN + xw];
-    const bool obst = (a.mask[(long long)(r - 1) * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+    p[2] = first ? a.halo_s[0 * a.pitch + x] : a.src[2 * PS + oS + x];
+    p[5] = first ? a.halo_s[1 * a.pitch + xw] : (sA ? a.side_src[2 * a.pitch + xw] : a.src[5 * PS + oS + xw]);
+    p[6] = first ? a.halo_s[2 * a.pitch + xe] : (sA ? a.side_src[3 * a.pitch + xe] : a.src[6 * PS + oS + xe]);
+    p[4] = last ? a.halo_n[0 * a.pitch + x] : a.src[4 * PS + oN + x];
+    p[7] = last ? a.halo_n[1 * a.pitch + xe] : (nA ? a.side_src[4 * a.pitch + xe] : a.src[7 * PS + oN + xe]);
+    p[8] = last ? a.halo_n[2 * a.pitch + xw] : (nA ? a.side_src[5 * a.pitch + xw] : a.src[8 * PS + oN + xw]);
+    const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
     const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
     q = to_fixed(s);
 #pragma unroll
     for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
-    if (r == a.accel_row) {
+    if (cA) {
       cell_accelerate<real, STRICT>(o[1], o[3], o[5], o[6], o[7], o[8], obst, a.aw1, a.aw2);
       a.side_dst[0 * a.pitch + x] = o[1]; a.side_dst[1 * a.pitch + x] = o[3];
       a.side_dst[2 * a.pitch + x] = o[5]; a.side_dst[3 * a.pitch + x] = o[6];
       a.side_dst[4 * a.pitch + x] = o[7]; a.side_dst[5 * a.pitch + x] = o[8];
     }
-    if (r == 1) {
-      a.dn_ghost[4 * a.dn_plane_stride + x] = o[4];
-      a.dn_ghost[7 * a.dn_plane_stride + x] = o[7];
-      a.dn_ghost[8 * a.dn_plane_stride + x] = o[8];
+    if (first) {
+      a.push_dn[0 * a.pitch + x] = o[4];
+      a.push_dn[1 * a.pitch + x] = o[7];
+      a.push_dn[2 * a.pitch + x] = o[8];
     }
-    if (r == a.rows) {
-      a.up_ghost[2 * a.up_plane_stride + x] = o[2];
-      a.up_ghost[5 * a.up_plane_stride + x] = o[5];
-      a.up_ghost[6 * a.up_plane_stride + x] = o[6];
+    if (last) {
+      a.push_up[0 * a.pitch + x] = o[2];
+      a.push_up[1 * a.pitch + x] = o[5];
+      a.push_up[2 * a.pitch + x] = o[6];
     }
   }
   block_accumulate(q, a.av_lo, a.av_hi);
@@ -500,9 +509,9 @@ struct PrepareArgs {
   const real* cur;            // current lattice buffer
   real* side_cur;             // side row of the same parity
   const uint32_t* mask;
-  real* up_ghost;             // neighbour above's ghost row 0 in its current buffer
-  real* dn_ghost;             // neighbour below's ghost row rows'+1
-  long long up_plane_stride, dn_plane_stride, plane_stride;
+  real* push_up;              // neighbour above's window, current parity, "from below"
+  real* push_dn;              // neighbour below's window, current parity, "from above"
+  long long plane_stride;
   int nx, rows, pitch, mask_pitch, accel_row;
   real aw1, aw2;
 };
@@ -515,14 +524,14 @@ __global__ void lbm_prepare(const PrepareArgs<real> a) {
 #pragma unroll 1
   for (int which = 0; which < 3; which++) {
     // 0: accelerate row -> side; 1: first row -> push down; 2: last row -> push up
-    const int r = (which == 0) ? a.accel_row : (which == 1 ? 1 : a.rows);
-    if (r < 1) continue;
+    const int r = (which == 0) ? a.accel_row : (which == 1 ? 0 : a.rows - 1);
+    if (r < 0) continue;
     const long long o = (long long)r * a.pitch + x;
     real f[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) f[k] = a.cur[k * PS + o];
     if (r == a.accel_row) {
-      const bool obst = (a.mask[(long long)(r - 1) * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+      const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
       cell_accelerate<real, true>(f[1], f[3], f[5], f[6], f[7], f[8], obst, a.aw1, a.aw2);
     }
     if (which == 0) {
@@ -530,13 +539,13 @@ __global__ void lbm_prepare(const PrepareArgs<real> a) {
       a.side_cur[2 * a.pitch + x] = f[5]; a.side_cur[3 * a.pitch + x] = f[6];
       a.side_cur[4 * a.pitch + x] = f[7]; a.side_cur[5 * a.pitch + x] = f[8];
     } else if (which == 1) {
-      a.dn_ghost[4 * a.dn_plane_stride + x] = f[4];
-      a.dn_ghost[7 * a.dn_plane_stride + x] = f[7];
-      a.dn_ghost[8 * a.dn_plane_stride + x] = f[8];
+      a.push_dn[0 * a.pitch + x] = f[4];
+      a.push_dn[1 * a.pitch + x] = f[7];
+      a.push_dn[2 * a.pitch + x] = f[8];
     } else {
-      a.up_ghost[2 * a.up_plane_stride + x] = f[2];
-      a.up_ghost[5 * a.up_plane_stride + x] = f[5];
-      a.up_ghost[6 * a.up_plane_stride + x] = f[6];
+      a.push_up[0 * a.pitch + x] = f[2];
+      a.push_up[1 * a.pitch + x] = f[5];
+      a.push_up[2 * a.pitch + x] = f[6];
     }
   }
 }
@@ -549,7 +558,7 @@ template <typename real>
 __global__ void lbm_init_rest(real* buf, long long plane_stride, int pitch, int nx, int rows,
                               real w0, real w1, real w2) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)(rows + 2) * pitch;
+  const long long total = (long long)rows * pitch;
   if (n >= total) return;
 #pragma unroll
   for (int k = 0; k < 9; k++) buf[k * plane_stride + n] = (k == 0) ? w0 : (k < 5 ? w1 : w2);
@@ -629,8 +638,8 @@ __global__ void lbm_fields(const real* __restrict__ buf, const uint32_t* __restr
   if (n < (long long)nrows * nx) {
     const int row = (int)(n / nx);
     const int x = (int)(n - (long long)row * nx);
-    const int r = r0 + row;                      // local row, 1-based
-    const bool obst = (mask[(long long)(r - 1) * mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+    const int r = r0 + row;                      // local row
+    const bool obst = (mask[(long long)r * mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
     real f[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) f[k] = buf[k * plane_stride + (long long)r * pitch + x];
