@@ -21,6 +21,7 @@ KERNEL_SCALAR = 4
 KERNEL_TMA = 8
 KERNEL_VEC4 = 16
 SYNC_FLAGS = 32
+KERNEL_PERSISTENT = 64
 IPC_DESC_BYTES = 256
 
 

@@ -68,7 +68,7 @@ static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large")
 constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
 
 enum SyncWord { kFlagFromBelow = 0, kFlagFromAbove = 1, kBoundaryDone = 2, kScratch0 = 3, kScratch1 = 4,
-                kScratch2 = 5, kSyncWords = 8 };
+                kScratch2 = 5, kGridBarrier = 6, kSyncWords = 8 };
 
 struct GridBase {
   virtual ~GridBase() {}
@@ -192,9 +192,53 @@ class Grid : public GridBase {
     mask_pitch = pitch / 32;
     if (flags & LBM_GPU_KERNEL_SCALAR) kernel = LBM_GPU_KERNEL_SCALAR;
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
-    else kernel = (nx % 4 == 0) ? LBM_GPU_KERNEL_VEC4 : LBM_GPU_KERNEL_SCALAR;
+    else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
+    else kernel = (nx % 4 == 0) ? LBM_GPU_KERNEL_VEC4 : LBM_GPU_KERNEL_SCALAR;   // refined in choose_kernel()
     if (kernel != LBM_GPU_KERNEL_SCALAR && nx % 4 != 0)
       throw CudaError{"the vector kernels need nx % 4 == 0"};
+    if (flags & LBM_GPU_KERNEL_TMA) throw CudaError{"LBM_GPU_KERNEL_TMA is reserved: no TMA kernel in this build"};
+  }
+
+  // launch shape shared by the step kernels: blockDim (bx, by), tiles of bx*vec x by cells
+  void tile_shape(int& vec, int& bx, int& by) const {
+    vec = (kernel == LBM_GPU_KERNEL_SCALAR) ? 1 : 4;
+    const int nxv = prm.nx / vec;
+    bx = (int)std::min<long long>(256, round_up(nxv, 32));
+    by = 256 / bx;
+  }
+
+  // blocks of lbm_steps_persistent that can be resident at once on the slab's GPU
+  int persistent_capacity(const Slab<real>& s) {
+    const bool strict = (flags & LBM_GPU_STRICT) != 0;
+    int per_sm = 0, sms = 0;
+    if (strict) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::lbm_steps_persistent<real, true>, 256, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::lbm_steps_persistent<real, false>, 256, 0));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
+    return coop ? per_sm * sms : 0;
+  }
+
+  // After the slabs exist: grids small enough to be launch-latency bound (they live in
+  // L2) run all their steps in one persistent cooperative kernel.
+  void choose_kernel() {
+    const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT);
+    if (kernel == LBM_GPU_KERNEL_PERSISTENT || (!forced && kernel == LBM_GPU_KERNEL_VEC4 && slabs.size() == 1 && !slab_mode)) {
+      if (slabs.size() != 1 || slab_mode) throw CudaError{"the persistent kernel handles a single slab only"};
+      CK(cudaSetDevice(slabs[0].device));
+      int vec, bx, by;
+      const int saved = kernel;
+      kernel = LBM_GPU_KERNEL_PERSISTENT;
+      tile_shape(vec, bx, by);
+      const long long tiles = (long long)((prm.nx / vec + bx - 1) / bx) * ((slabs[0].rows + by - 1) / by);
+      const int cap = persistent_capacity(slabs[0]);
+      if (cap < 1) {
+        if (forced) throw CudaError{"cooperative launch is not available on this device"};
+        kernel = saved;
+      } else if (!forced && tiles > 4LL * cap) {
+        kernel = saved;           // large grid: bandwidth bound, one launch per step is free
+      }
+    }
   }
 
   // ------------------------------------------------------------- lattice input ----
@@ -348,12 +392,43 @@ class Grid : public GridBase {
     }
     for (auto& s : slabs) { CK(cudaSetDevice(s.device)); CK(cudaEventRecord(s.ev0, s.stream)); }
 
-    const int vec = (kernel == LBM_GPU_KERNEL_SCALAR) ? 1 : 4;
+    int vec, bx, by;
+    tile_shape(vec, bx, by);
     const int nxv = prm.nx / vec;
-    const int bx = (int)std::min<long long>(256, round_up(nxv, 32));
-    const int by = 256 / bx;
     const dim3 block(bx, by);
-    for (int t = 0; t < n_steps; t++) {
+    if (kernel == LBM_GPU_KERNEL_PERSISTENT) {
+      Slab<real>& s = slabs[0];
+      CK(cudaSetDevice(s.device));
+      lbm::PersistArgs<real> pa;
+      memset(&pa, 0, sizeof pa);
+      lbm::StepArgs<real>& a = pa.s;
+      a.mask = s.mask;
+      a.plane_stride = plane_stride(s);
+      a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch;
+      a.accel_row = s.accel_row;
+      a.tiles_x = (nxv + bx - 1) / bx;
+      a.tiles_y = (s.rows + by - 1) / by;
+      a.omega = prm.omega;
+      a.aw1 = prm.density * prm.accel / (real)9;
+      a.aw2 = prm.density * prm.accel / (real)36;
+      for (int b = 0; b < 2; b++) { pa.lattice[b] = s.lattice[b]; pa.side[b] = s.side[b]; }
+      pa.window = (real*)s.win;
+      pa.av_lo = s.av_lo;
+      pa.av_hi = s.av_hi;
+      pa.barrier = s.sync + kGridBarrier;
+      pa.first_parity = (int)(steps_done & 1);
+      pa.n_steps = n_steps;
+      pa.n_tiles = a.tiles_x * a.tiles_y;
+      const int cap = persistent_capacity(s);
+      const int rounds = (pa.n_tiles + cap - 1) / cap;
+      const int nblocks = (pa.n_tiles + rounds - 1) / rounds;
+      CK(cudaMemsetAsync(pa.barrier, 0, sizeof(unsigned long long), s.stream));
+      void* kargs[] = {(void*)&pa};
+      if (strict) CK(cudaLaunchCooperativeKernel((void*)lbm::lbm_steps_persistent<real, true>, dim3(nblocks), block, kargs, 0, s.stream));
+      else CK(cudaLaunchCooperativeKernel((void*)lbm::lbm_steps_persistent<real, false>, dim3(nblocks), block, kargs, 0, s.stream));
+      launches++;
+    }
+    for (int t = 0; t < n_steps && kernel != LBM_GPU_KERNEL_PERSISTENT; t++) {
       const unsigned long long step = (unsigned long long)(steps_done + t);
       const int src = (int)(step & 1), dst = src ^ 1;
       const int nslabs = (int)slabs.size();
@@ -568,6 +643,7 @@ int create_impl(const typename ParamT<real>::type* params, const real* cells_aos
                    obstacles ? (const char*)obstacles + (size_t)s.row0 * obst_row_bytes : nullptr, 0);
     }
     g->connect_local();
+    g->choose_kernel();
     g->prepare();
   } catch (const CudaError& e) {
     return fail("lbm_gpu_create: %s", e.what.c_str());
@@ -665,6 +741,7 @@ int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows
     s.accel_row = (ar >= row0 && ar < row0 + nrows) ? (int)(ar - row0) : LBM_NO_ROW;
     g->alloc_slab(s);
     g->load_slab(s, cells_aos_rows, obstacles_rows, 0);
+    if (g->kernel == LBM_GPU_KERNEL_PERSISTENT) throw CudaError{"the persistent kernel handles a single slab only"};
     if (nrows == params->ny) { g->connect_local(); g->prepare(); }   // whole grid in one slab
   } catch (const CudaError& e) {
     return fail("lbm_gpu_create_slab: %s", e.what.c_str());

@@ -240,6 +240,24 @@ __device__ __forceinline__ Vec4<real> ld4(const real* p) { return *reinterpret_c
 template <typename real>
 __device__ __forceinline__ void st4(real* p, const Vec4<real>& v) { *reinterpret_cast<Vec4<real>*>(p) = v; }
 
+// L2-only loads (ld.global.cg): the persistent kernel re-reads, step after step, memory
+// that other SMs wrote in the previous step, so nothing may be served from a stale L1 line.
+__device__ __forceinline__ Vec4<float> ld4cg(const float* p) {
+  const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+  Vec4<float> v; v.x = t.x; v.y = t.y; v.z = t.z; v.w = t.w;
+  return v;
+}
+__device__ __forceinline__ Vec4<double> ld4cg(const double* p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  Vec4<double> v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
+  return v;
+}
+template <typename real, bool CG>
+__device__ __forceinline__ Vec4<real> load4(const real* p) { return CG ? ld4cg(p) : ld4(p); }
+template <typename real, bool CG>
+__device__ __forceinline__ real load1(const real* p) { return CG ? __ldcg(p) : *p; }
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const volatile unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -317,14 +335,8 @@ __device__ __forceinline__ void boundary_signal(const StepArgs<real>& a, const b
 // that element with a scalar load that also implements the periodic wrap in x.
 // blockDim = (BX, BY), BX a multiple of 32 so that a warp never spans two rows.
 // ------------------------------------------------------------------------------------
-template <typename real, bool STRICT, bool MULTI>
-__global__ void __launch_bounds__(256)
-lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
-  int tx, ty;
-  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
-  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
-  boundary_wait<real, MULTI>(a, is_boundary);
-
+template <typename real, bool STRICT, bool CG>
+__device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a, const int tx, const int ty) {
   const int x0 = (tx * (int)blockDim.x + (int)threadIdx.x) * 4;
   const int r = ty * (int)blockDim.y + (int)threadIdx.y;        // local row
   const bool active = (x0 < a.nx) && (r < a.rows);
@@ -360,12 +372,12 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   const int xw = (xc == 0) ? a.nx - 1 : xc - 1;
   const int xe = (xc + 4 >= a.nx) ? 0 : xc + 4;
   real w1e = 0, w5e = 0, w8e = 0, e3e = 0, e6e = 0, e7e = 0;
-  if (need_w) { w1e = p1[xw]; w5e = p5[xw]; w8e = p8[xw]; }
-  if (need_e) { e3e = p3[xe]; e6e = p6[xe]; e7e = p7[xe]; }
+  if (need_w) { w1e = load1<real, CG>(p1 + xw); w5e = load1<real, CG>(p5 + xw); w8e = load1<real, CG>(p8 + xw); }
+  if (need_e) { e3e = load1<real, CG>(p3 + xe); e6e = load1<real, CG>(p6 + xe); e7e = load1<real, CG>(p7 + xe); }
 
-  const Vec4<real> v0 = ld4(p0 + xc), v1 = ld4(p1 + xc), v2 = ld4(p2 + xc), v3 = ld4(p3 + xc),
-                   v4 = ld4(p4 + xc), v5 = ld4(p5 + xc), v6 = ld4(p6 + xc), v7 = ld4(p7 + xc),
-                   v8 = ld4(p8 + xc);
+  const Vec4<real> v0 = load4<real, CG>(p0 + xc), v1 = load4<real, CG>(p1 + xc), v2 = load4<real, CG>(p2 + xc),
+                   v3 = load4<real, CG>(p3 + xc), v4 = load4<real, CG>(p4 + xc), v5 = load4<real, CG>(p5 + xc),
+                   v6 = load4<real, CG>(p6 + xc), v7 = load4<real, CG>(p7 + xc), v8 = load4<real, CG>(p8 + xc);
   const uint32_t mword = a.mask[(long long)rc * a.mask_pitch + (xc >> 5)];
   const uint32_t mbits = (mword >> (xc & 31)) & 0xFu;
 
@@ -435,8 +447,85 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   } else {
     q = 0ULL;
   }
+  return q;
+}
+
+template <typename real, bool STRICT, bool MULTI>
+__global__ void __launch_bounds__(256)
+lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
+  int tx, ty;
+  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  boundary_wait<real, MULTI>(a, is_boundary);
+  const unsigned long long q = vec4_tile<real, STRICT, false>(a, tx, ty);
   block_accumulate(q, a.av_lo, a.av_hi);
   boundary_signal<real, MULTI>(a, is_boundary);
+}
+
+// ------------------------------------------------------------------------------------
+// K5  lbm_steps_persistent: ALL timesteps of a run in one cooperative launch, for grids
+// small enough to live in L2 (the reference's shipped inputs: 0.6-38 MB per buffer).
+// There the per-step cost of K1a is launch latency, not bandwidth.  Every block owns a
+// fixed set of tiles, loops over the steps, and meets the other blocks at a grid barrier
+// (one atomic per block) between steps; buffers swap roles inside the kernel.  Single
+// slab only (the halo window is the slab's own).  Loads are L2-only (see ld4cg).
+// Must be launched with cudaLaunchCooperativeKernel so that all blocks are resident.
+// ------------------------------------------------------------------------------------
+template <typename real>
+struct PersistArgs {
+  StepArgs<real> s;            // geometry, constants and the step-0 pointers
+  real* lattice[2];
+  real* side[2];
+  real* window;                // own window: section (parity b, direction d) at ((b*2+d)*3)*pitch
+  unsigned long long* av_lo;   // n_steps entries
+  unsigned long long* av_hi;
+  unsigned long long* barrier; // zeroed before the launch
+  int first_parity;            // buffer index read by the first step
+  int n_steps;
+  int n_tiles;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, const unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    atomicAdd(counter, 1ULL);
+    while (ld_acquire_gpu(counter) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename real, bool STRICT>
+__global__ void __launch_bounds__(256)
+lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
+  StepArgs<real> a = pa.s;
+  const int pitch = a.pitch;
+  for (int t = 0; t < pa.n_steps; t++) {
+    const int src = (pa.first_parity + t) & 1, dst = src ^ 1;
+    a.src = pa.lattice[src];
+    a.dst = pa.lattice[dst];
+    a.side_src = pa.side[src];
+    a.side_dst = pa.side[dst];
+    a.halo_s = pa.window + (size_t)((src * 2 + 0) * 3) * pitch;
+    a.halo_n = pa.window + (size_t)((src * 2 + 1) * 3) * pitch;
+    a.push_up = pa.window + (size_t)((dst * 2 + 0) * 3) * pitch;
+    a.push_dn = pa.window + (size_t)((dst * 2 + 1) * 3) * pitch;
+    unsigned long long q = 0ULL;
+    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
+      const int ty = tile / a.tiles_x;
+      const int tx = tile - ty * a.tiles_x;
+      q += vec4_tile<real, STRICT, true>(a, tx, ty);
+    }
+    block_accumulate(q, pa.av_lo + t, pa.av_hi + t);
+    grid_barrier(pa.barrier, (unsigned long long)gridDim.x * (unsigned long long)(t + 1));
+  }
 }
 
 // ------------------------------------------------------------------------------------

@@ -65,6 +65,9 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
 #define LBM_GPU_KERNEL_SCALAR  4u  /* force the one-cell-per-thread kernel (any nx) */
 #define LBM_GPU_KERNEL_TMA     8u  /* force the TMA-staged kernel (needs nx % 4 == 0) */
 #define LBM_GPU_KERNEL_VEC4   16u  /* force the 128-bit direct-load kernel (nx % 4 == 0) */
+#define LBM_GPU_KERNEL_PERSISTENT 64u /* force the persistent cooperative kernel (all steps of a run
+                                      in one launch; single GPU, nx % 4 == 0).  Chosen by default
+                                      for grids small enough to live in L2 */
 #define LBM_GPU_SYNC_FLAGS    32u  /* lbm_gpu_create with n_gpus > 1: order the slabs with the
                                       device-side flag protocol of the one-process-per-GPU form
                                       instead of CUDA events (every slab on its own GPU) */

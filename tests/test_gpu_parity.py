@@ -28,7 +28,7 @@ ODD_SHAPES = [(1, 2), (3, 5), (37, 11), (129, 4), (250, 9), (33, 2)]
 
 
 def _kernels_for(nx):
-    return [L.KERNEL_SCALAR] + ([L.KERNEL_VEC4] if nx % 4 == 0 else [])
+    return [L.KERNEL_SCALAR] + ([L.KERNEL_VEC4, L.KERNEL_PERSISTENT] if nx % 4 == 0 else [])
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES + ODD_SHAPES)
@@ -79,18 +79,39 @@ def test_rest_state_and_obstacle_bits():
     assert np.array_equal(b, ref)
 
 
-def test_chunked_runs_equal_one_run():
+@pytest.mark.parametrize("kernel", ["vec4", "persistent", "scalar"])
+def test_chunked_runs_equal_one_run(kernel):
     """run(a); run(b) == run(a+b): no state is lost between calls (odd and even splits)."""
+    k = {"vec4": L.KERNEL_VEC4, "persistent": L.KERNEL_PERSISTENT, "scalar": L.KERNEL_SCALAR}[kernel]
     nx, ny = 128, 24
     cells, obst = O.random_lattice(nx, ny, seed=11)
-    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst) as lat:
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
         av_all = lat.run(9)
         one = lat.download()
-    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst) as lat:
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
         av_parts = np.concatenate([lat.run(1), lat.run(3), lat.run(0), lat.run(5)])
         parts = lat.download()
     assert np.array_equal(one, parts)
     assert np.array_equal(av_all, av_parts)
+
+
+def test_kernel_selection():
+    """Small single-GPU grids take the persistent kernel, big ones one launch per step,
+    widths that are not a multiple of 4 the scalar kernel; all give the same bits."""
+    with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA) as lat:
+        assert lat.info().kernel == L.KERNEL_PERSISTENT
+    with L.Lattice(130, 16, DENSITY, ACCEL, OMEGA) as lat:
+        assert lat.info().kernel == L.KERNEL_SCALAR
+    with L.Lattice(4096, 4096, DENSITY, ACCEL, OMEGA) as lat:
+        assert lat.info().kernel == L.KERNEL_VEC4
+    nx, ny = 1024, 600          # more tiles than resident blocks: every block loops
+    cells, obst = O.random_lattice(nx, ny, seed=13, p_obst=0.01)
+    res = []
+    for k in (L.KERNEL_VEC4, L.KERNEL_PERSISTENT):
+        with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
+            av = lat.run(7)
+            res.append((lat.download(), av))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
 
 
 def test_final_fields_and_av_velocity():
@@ -129,7 +150,7 @@ def test_f64_kernel_matches_f64_oracle():
     nx, ny = 128, 16
     cells, obst = O.random_lattice(nx, ny, seed=4, dtype=np.float64)
     ref, av_ref, _ = O.run(cells, obst, 10, DENSITY, ACCEL, OMEGA)
-    for k in (L.KERNEL_SCALAR, L.KERNEL_VEC4):
+    for k in (L.KERNEL_SCALAR, L.KERNEL_VEC4, L.KERNEL_PERSISTENT):
         with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, f64=True,
                        flags=L.STRICT | k) as lat:
             av = lat.run(10)

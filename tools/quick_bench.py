@@ -20,7 +20,7 @@ ap.add_argument("--kernel", default="auto")
 ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--f64", action="store_true")
 a = ap.parse_args()
-flags = {"auto": 0, "scalar": L.KERNEL_SCALAR, "vec4": L.KERNEL_VEC4, "tma": L.KERNEL_TMA}[a.kernel]
+flags = {"auto": 0, "scalar": L.KERNEL_SCALAR, "vec4": L.KERNEL_VEC4, "tma": L.KERNEL_TMA, "persistent": L.KERNEL_PERSISTENT}[a.kernel]
 t0 = time.time()
 mask = channel_mask(a.nx, a.ny)
 bits = L.pack_obstacle_bits(mask)
