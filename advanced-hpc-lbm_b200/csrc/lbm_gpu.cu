@@ -118,6 +118,7 @@ class Grid : public GridBase {
   Param prm;
   unsigned flags = 0;
   int kernel = 0;
+  int persistent_vec = 4;      // cells per thread of the persistent kernel (4, or 1 for tiny grids)
   int pitch = 0, mask_pitch = 0;
   bool slab_mode = false;      // one process per GPU: neighbours are other processes
   bool connected = false;      // neighbour views are set
@@ -194,27 +195,31 @@ class Grid : public GridBase {
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
     else kernel = (nx % 4 == 0) ? LBM_GPU_KERNEL_VEC4 : LBM_GPU_KERNEL_SCALAR;   // refined in choose_kernel()
-    if (kernel != LBM_GPU_KERNEL_SCALAR && nx % 4 != 0)
-      throw CudaError{"the vector kernels need nx % 4 == 0"};
+    if (kernel == LBM_GPU_KERNEL_VEC4 && nx % 4 != 0)
+      throw CudaError{"the vector kernel needs nx % 4 == 0"};
     if (flags & LBM_GPU_KERNEL_TMA) throw CudaError{"LBM_GPU_KERNEL_TMA is reserved: no TMA kernel in this build"};
   }
 
   // launch shape shared by the step kernels: blockDim (bx, by), tiles of bx*vec x by cells
   void tile_shape(int& vec, int& bx, int& by) const {
-    vec = (kernel == LBM_GPU_KERNEL_SCALAR) ? 1 : 4;
+    vec = (kernel == LBM_GPU_KERNEL_SCALAR || (kernel == LBM_GPU_KERNEL_PERSISTENT && persistent_vec == 1)) ? 1 : 4;
     const int nxv = prm.nx / vec;
     bx = (int)std::min<long long>(256, round_up(nxv, 32));
     by = 256 / bx;
   }
 
   // blocks of lbm_steps_persistent that can be resident at once on the slab's GPU
-  int persistent_capacity(const Slab<real>& s) {
+  const void* persistent_fn() const {
     const bool strict = (flags & LBM_GPU_STRICT) != 0;
-    int per_sm = 0, sms = 0;
-    if (strict) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::lbm_steps_persistent<real, true>, 256, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::lbm_steps_persistent<real, false>, 256, 0));
+    if (persistent_vec == 1)
+      return strict ? (const void*)lbm::lbm_steps_persistent<real, true, 1> : (const void*)lbm::lbm_steps_persistent<real, false, 1>;
+    return strict ? (const void*)lbm::lbm_steps_persistent<real, true, 4> : (const void*)lbm::lbm_steps_persistent<real, false, 4>;
+  }
+
+  int persistent_capacity(const Slab<real>& s) {
+    int per_sm = 0, sms = 0, coop = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_fn(), 256, 0));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
-    int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
     return coop ? per_sm * sms : 0;
   }
@@ -223,21 +228,30 @@ class Grid : public GridBase {
   // L2) run all their steps in one persistent cooperative kernel.
   void choose_kernel() {
     const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT);
-    if (kernel == LBM_GPU_KERNEL_PERSISTENT || (!forced && kernel == LBM_GPU_KERNEL_VEC4 && slabs.size() == 1 && !slab_mode)) {
-      if (slabs.size() != 1 || slab_mode) throw CudaError{"the persistent kernel handles a single slab only"};
-      CK(cudaSetDevice(slabs[0].device));
+    const bool want = (kernel == LBM_GPU_KERNEL_PERSISTENT);
+    if (!want && (forced || slabs.size() != 1 || slab_mode)) return;
+    if (slabs.size() != 1 || slab_mode) throw CudaError{"the persistent kernel handles a single slab only"};
+    CK(cudaSetDevice(slabs[0].device));
+    const int saved = kernel;
+    kernel = LBM_GPU_KERNEL_PERSISTENT;
+    auto tiles_for = [&](int pv) {
+      persistent_vec = pv;
       int vec, bx, by;
-      const int saved = kernel;
-      kernel = LBM_GPU_KERNEL_PERSISTENT;
       tile_shape(vec, bx, by);
-      const long long tiles = (long long)((prm.nx / vec + bx - 1) / bx) * ((slabs[0].rows + by - 1) / by);
-      const int cap = persistent_capacity(slabs[0]);
-      if (cap < 1) {
-        if (forced) throw CudaError{"cooperative launch is not available on this device"};
-        kernel = saved;
-      } else if (!forced && tiles > 4LL * cap) {
-        kernel = saved;           // large grid: bandwidth bound, one launch per step is free
-      }
+      return (long long)((prm.nx / vec + bx - 1) / bx) * ((slabs[0].rows + by - 1) / by);
+    };
+    // tiny grids: one cell per thread if all of those tiles can be resident at once
+    long long tiles = tiles_for(1);
+    int cap = persistent_capacity(slabs[0]);
+    if (tiles > cap && prm.nx % 4 == 0) {
+      tiles = tiles_for(4);
+      cap = persistent_capacity(slabs[0]);
+    }
+    if (cap < 1) {
+      if (want) throw CudaError{"cooperative launch is not available on this device"};
+      kernel = saved;
+    } else if (!want && tiles > 4LL * cap) {
+      kernel = saved;             // large grid: bandwidth bound, one launch per step is free
     }
   }
 
@@ -424,8 +438,7 @@ class Grid : public GridBase {
       const int nblocks = (pa.n_tiles + rounds - 1) / rounds;
       CK(cudaMemsetAsync(pa.barrier, 0, sizeof(unsigned long long), s.stream));
       void* kargs[] = {(void*)&pa};
-      if (strict) CK(cudaLaunchCooperativeKernel((void*)lbm::lbm_steps_persistent<real, true>, dim3(nblocks), block, kargs, 0, s.stream));
-      else CK(cudaLaunchCooperativeKernel((void*)lbm::lbm_steps_persistent<real, false>, dim3(nblocks), block, kargs, 0, s.stream));
+      CK(cudaLaunchCooperativeKernel(persistent_fn(), dim3(nblocks), block, kargs, 0, s.stream));
       launches++;
     }
     for (int t = 0; t < n_steps && kernel != LBM_GPU_KERNEL_PERSISTENT; t++) {

@@ -463,12 +463,80 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
 }
 
 // ------------------------------------------------------------------------------------
+// K1b  lbm_step_scalar: one cell per thread, any nx.  Same arithmetic; used for grids
+// whose width is not a multiple of 4 and as an independent cross-check of K1a.
+// ------------------------------------------------------------------------------------
+template <typename real, bool STRICT, bool CG>
+__device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& a, const int tx, const int ty) {
+#define LD(ptr) load1<real, CG>(ptr)
+  const int x = tx * (int)blockDim.x + (int)threadIdx.x;
+  const int r = ty * (int)blockDim.y + (int)threadIdx.y;
+  const bool active = (x < a.nx) && (r < a.rows);
+  unsigned long long q = 0ULL;
+  if (active) {
+    const long long PS = a.plane_stride;
+    const long long oC = (long long)r * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
+    const bool first = (r == 0), last = (r == a.rows - 1);
+    const bool cA = (r == a.accel_row), sA = (r - 1 == a.accel_row), nA = (r + 1 == a.accel_row);
+    const int xw = (x == 0) ? a.nx - 1 : x - 1;
+    const int xe = (x + 1 == a.nx) ? 0 : x + 1;
+    real p[9], o[9];
+    p[0] = LD(a.src + oC + x);
+    p[1] = cA ? LD(a.side_src + 0 * a.pitch + xw) : LD(a.src + 1 * PS + oC + xw);
+    p[3] = cA ? LD(a.side_src + 1 * a.pitch + xe) : LD(a.src + 3 * PS + oC + xe);
+    p[2] = first ? LD(a.halo_s + 0 * a.pitch + x) : LD(a.src + 2 * PS + oS + x);
+    p[5] = first ? LD(a.halo_s + 1 * a.pitch + xw) : (sA ? LD(a.side_src + 2 * a.pitch + xw) : LD(a.src + 5 * PS + oS + xw));
+    p[6] = first ? LD(a.halo_s + 2 * a.pitch + xe) : (sA ? LD(a.side_src + 3 * a.pitch + xe) : LD(a.src + 6 * PS + oS + xe));
+    p[4] = last ? LD(a.halo_n + 0 * a.pitch + x) : LD(a.src + 4 * PS + oN + x);
+    p[7] = last ? LD(a.halo_n + 1 * a.pitch + xe) : (nA ? LD(a.side_src + 4 * a.pitch + xe) : LD(a.src + 7 * PS + oN + xe));
+    p[8] = last ? LD(a.halo_n + 2 * a.pitch + xw) : (nA ? LD(a.side_src + 5 * a.pitch + xw) : LD(a.src + 8 * PS + oN + xw));
+    const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
+    const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
+    q = to_fixed(s);
+#pragma unroll
+    for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
+    if (cA) {
+      cell_accelerate<real, STRICT>(o[1], o[3], o[5], o[6], o[7], o[8], obst, a.aw1, a.aw2);
+      a.side_dst[0 * a.pitch + x] = o[1]; a.side_dst[1 * a.pitch + x] = o[3];
+      a.side_dst[2 * a.pitch + x] = o[5]; a.side_dst[3 * a.pitch + x] = o[6];
+      a.side_dst[4 * a.pitch + x] = o[7]; a.side_dst[5 * a.pitch + x] = o[8];
+    }
+    if (first) {
+      a.push_dn[0 * a.pitch + x] = o[4];
+      a.push_dn[1 * a.pitch + x] = o[7];
+      a.push_dn[2 * a.pitch + x] = o[8];
+    }
+    if (last) {
+      a.push_up[0 * a.pitch + x] = o[2];
+      a.push_up[1 * a.pitch + x] = o[5];
+      a.push_up[2 * a.pitch + x] = o[6];
+    }
+  }
+#undef LD
+  return q;
+}
+
+template <typename real, bool STRICT, bool MULTI>
+__global__ void __launch_bounds__(256)
+lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
+  int tx, ty;
+  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  boundary_wait<real, MULTI>(a, is_boundary);
+  const unsigned long long q = scalar_tile<real, STRICT, false>(a, tx, ty);
+  block_accumulate(q, a.av_lo, a.av_hi);
+  boundary_signal<real, MULTI>(a, is_boundary);
+}
+
+// ------------------------------------------------------------------------------------
 // K5  lbm_steps_persistent: ALL timesteps of a run in one cooperative launch, for grids
 // small enough to live in L2 (the reference's shipped inputs: 0.6-38 MB per buffer).
 // There the per-step cost of K1a is launch latency, not bandwidth.  Every block owns a
 // fixed set of tiles, loops over the steps, and meets the other blocks at a grid barrier
 // (one atomic per block) between steps; buffers swap roles inside the kernel.  Single
 // slab only (the halo window is the slab's own).  Loads are L2-only (see ld4cg).
+// VEC = 4 cells per thread (K1a's tile) or, for the smallest grids, 1 cell per thread
+// (K1b's tile): four times as many threads share the step's dependent-latency chain.
 // Must be launched with cudaLaunchCooperativeKernel so that all blocks are resident.
 // ------------------------------------------------------------------------------------
 template <typename real>
@@ -502,7 +570,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, const 
   __syncthreads();
 }
 
-template <typename real, bool STRICT>
+template <typename real, bool STRICT, int VEC>
 __global__ void __launch_bounds__(256)
 lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
   StepArgs<real> a = pa.s;
@@ -521,70 +589,11 @@ lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
     for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
       const int ty = tile / a.tiles_x;
       const int tx = tile - ty * a.tiles_x;
-      q += vec4_tile<real, STRICT, true>(a, tx, ty);
+      q += (VEC == 4) ? vec4_tile<real, STRICT, true>(a, tx, ty) : scalar_tile<real, STRICT, true>(a, tx, ty);
     }
     block_accumulate(q, pa.av_lo + t, pa.av_hi + t);
     grid_barrier(pa.barrier, (unsigned long long)gridDim.x * (unsigned long long)(t + 1));
   }
-}
-
-// ------------------------------------------------------------------------------------
-// K1b  lbm_step_scalar: one cell per thread, any nx.  Same arithmetic; used for grids
-// whose width is not a multiple of 4 and as an independent cross-check of K1a.
-// ------------------------------------------------------------------------------------
-template <typename real, bool STRICT, bool MULTI>
-__global__ void __launch_bounds__(256)
-lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
-  int tx, ty;
-  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
-  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
-  boundary_wait<real, MULTI>(a, is_boundary);
-
-  const int x = tx * (int)blockDim.x + (int)threadIdx.x;
-  const int r = ty * (int)blockDim.y + (int)threadIdx.y;
-  const bool active = (x < a.nx) && (r < a.rows);
-  unsigned long long q = 0ULL;
-  if (active) {
-    const long long PS = a.plane_stride;
-    const long long oC = (long long)r * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
-    const bool first = (r == 0), last = (r == a.rows - 1);
-    const bool cA = (r == a.accel_row), sA = (r - 1 == a.accel_row), nA = (r + 1 == a.accel_row);
-    const int xw = (x == 0) ? a.nx - 1 : x - 1;
-    const int xe = (x + 1 == a.nx) ? 0 : x + 1;
-    real p[9], o[9];
-    p[0] = a.src[oC + x];
-    p[1] = cA ? a.side_src[0 * a.pitch + xw] : a.src[1 * PS + oC + xw];
-    p[3] = cA ? a.side_src[1 * a.pitch + xe] : a.src[3 * PS + oC + xe];
-    p[2] = first ? a.halo_s[0 * a.pitch + x] : a.src[2 * PS + oS + x];
-    p[5] = first ? a.halo_s[1 * a.pitch + xw] : (sA ? a.side_src[2 * a.pitch + xw] : a.src[5 * PS + oS + xw]);
-    p[6] = first ? a.halo_s[2 * a.pitch + xe] : (sA ? a.side_src[3 * a.pitch + xe] : a.src[6 * PS + oS + xe]);
-    p[4] = last ? a.halo_n[0 * a.pitch + x] : a.src[4 * PS + oN + x];
-    p[7] = last ? a.halo_n[1 * a.pitch + xe] : (nA ? a.side_src[4 * a.pitch + xe] : a.src[7 * PS + oN + xe]);
-    p[8] = last ? a.halo_n[2 * a.pitch + xw] : (nA ? a.side_src[5 * a.pitch + xw] : a.src[8 * PS + oN + xw]);
-    const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
-    const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
-    q = to_fixed(s);
-#pragma unroll
-    for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
-    if (cA) {
-      cell_accelerate<real, STRICT>(o[1], o[3], o[5], o[6], o[7], o[8], obst, a.aw1, a.aw2);
-      a.side_dst[0 * a.pitch + x] = o[1]; a.side_dst[1 * a.pitch + x] = o[3];
-      a.side_dst[2 * a.pitch + x] = o[5]; a.side_dst[3 * a.pitch + x] = o[6];
-      a.side_dst[4 * a.pitch + x] = o[7]; a.side_dst[5 * a.pitch + x] = o[8];
-    }
-    if (first) {
-      a.push_dn[0 * a.pitch + x] = o[4];
-      a.push_dn[1 * a.pitch + x] = o[7];
-      a.push_dn[2 * a.pitch + x] = o[8];
-    }
-    if (last) {
-      a.push_up[0 * a.pitch + x] = o[2];
-      a.push_up[1 * a.pitch + x] = o[5];
-      a.push_up[2 * a.pitch + x] = o[6];
-    }
-  }
-  block_accumulate(q, a.av_lo, a.av_hi);
-  boundary_signal<real, MULTI>(a, is_boundary);
 }
 
 // ------------------------------------------------------------------------------------

@@ -193,6 +193,8 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
     per_step_budget = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    if os.environ.get("LBM_BENCH_CPU_BUDGET_S"):          # tests: shorter CPU sample
+        per_step_budget = float(os.environ["LBM_BENCH_CPU_BUDGET_S"])
     for _ in range(args.warmup):
         cpu_reference_mlups(per_step_budget / 4)
     vals, tot_updates, tot_time = [], 0.0, 0.0

@@ -28,7 +28,7 @@ ODD_SHAPES = [(1, 2), (3, 5), (37, 11), (129, 4), (250, 9), (33, 2)]
 
 
 def _kernels_for(nx):
-    return [L.KERNEL_SCALAR] + ([L.KERNEL_VEC4, L.KERNEL_PERSISTENT] if nx % 4 == 0 else [])
+    return [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT] + ([L.KERNEL_VEC4] if nx % 4 == 0 else [])
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES + ODD_SHAPES)
@@ -101,6 +101,8 @@ def test_kernel_selection():
     with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_PERSISTENT
     with L.Lattice(130, 16, DENSITY, ACCEL, OMEGA) as lat:
+        assert lat.info().kernel == L.KERNEL_PERSISTENT          # one cell per thread
+    with L.Lattice(4098, 4096, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_SCALAR
     with L.Lattice(4096, 4096, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_VEC4
