@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblbm_b200.so")
+# LBM_B200_LIB selects another build of the same ABI (kernel tuning variants, tools/build_variants.py)
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "liblbm_b200.so")
 
 # lbm_gpu_create flags (include/lbm_gpu.h)
 STRICT = 1

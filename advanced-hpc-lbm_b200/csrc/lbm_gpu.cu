@@ -204,8 +204,8 @@ class Grid : public GridBase {
   void tile_shape(int& vec, int& bx, int& by) const {
     vec = (kernel == LBM_GPU_KERNEL_SCALAR || (kernel == LBM_GPU_KERNEL_PERSISTENT && persistent_vec == 1)) ? 1 : 4;
     const int nxv = prm.nx / vec;
-    bx = (int)std::min<long long>(256, round_up(nxv, 32));
-    by = 256 / bx;
+    bx = (int)std::min<long long>(LBM_BLOCK_THREADS, round_up(nxv, 32));
+    by = LBM_BLOCK_THREADS / bx;
   }
 
   // blocks of lbm_steps_persistent that can be resident at once on the slab's GPU
@@ -218,7 +218,7 @@ class Grid : public GridBase {
 
   int persistent_capacity(const Slab<real>& s) {
     int per_sm = 0, sms = 0, coop = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_fn(), 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_fn(), LBM_BLOCK_THREADS, 0));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
     return coop ? per_sm * sms : 0;

@@ -23,6 +23,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Compile-time tuning knobs of the step kernels (defaults = the measured best, see
+// profiles/r01_kernel_variants.md; tools/build_variants.py builds the alternatives).
+#ifndef LBM_BLOCK_THREADS
+#define LBM_BLOCK_THREADS 256       // threads per block of K1a/K1b/K5
+#endif
+#ifndef LBM_MIN_BLOCKS
+#define LBM_MIN_BLOCKS 4            // K1a fp32: 4 blocks/SM (64 registers, 56 B spilled) measured +7 %
+#endif                              // over 3 blocks/SM (80 registers): hides the av reduction barrier
+#ifndef LBM_LOAD_MODE
+#define LBM_LOAD_MODE 0             // 0 plain, 1 ld.global.cs (evict-first), 2 ld.global.nc, 3 nc + L1::no_allocate
+#endif
+#ifndef LBM_PERSIST_MIN_BLOCKS
+#define LBM_PERSIST_MIN_BLOCKS 3    // K5: keeps it at <= 85 registers so 3 blocks/SM are resident
+#endif
+#ifndef LBM_AV_MODE
+#define LBM_AV_MODE 0               // 0 block reduction + one atomic per block; 1 = NO av sums (experiment only)
+#endif
+#ifndef LBM_STORE_MODE
+#define LBM_STORE_MODE 0            // 0 plain, 1 st.global.cs (streaming), 2 st.global.cg
+#endif
+
 namespace lbm {
 
 // ------------------------------------------------------------------------------------
@@ -235,10 +256,32 @@ struct StepArgs {
 
 template <typename real> struct alignas(4 * sizeof(real)) Vec4 { real x, y, z, w; };
 
-template <typename real>
-__device__ __forceinline__ Vec4<real> ld4(const real* p) { return *reinterpret_cast<const Vec4<real>*>(p); }
-template <typename real>
-__device__ __forceinline__ void st4(real* p, const Vec4<real>& v) { *reinterpret_cast<Vec4<real>*>(p) = v; }
+__device__ __forceinline__ Vec4<float> ld4(const float* p) {
+#if LBM_LOAD_MODE == 1
+  const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+#elif LBM_LOAD_MODE == 2
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+#elif LBM_LOAD_MODE == 3
+  float4 t;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p));
+#else
+  const float4 t = *reinterpret_cast<const float4*>(p);
+#endif
+  Vec4<float> v; v.x = t.x; v.y = t.y; v.z = t.z; v.w = t.w;
+  return v;
+}
+__device__ __forceinline__ Vec4<double> ld4(const double* p) { return *reinterpret_cast<const Vec4<double>*>(p); }
+__device__ __forceinline__ void st4(float* p, const Vec4<float>& v) {
+#if LBM_STORE_MODE == 1
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w));
+#elif LBM_STORE_MODE == 2
+  __stcg(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w));
+#else
+  *reinterpret_cast<Vec4<float>*>(p) = v;
+#endif
+}
+__device__ __forceinline__ void st4(double* p, const Vec4<double>& v) { *reinterpret_cast<Vec4<double>*>(p) = v; }
 
 // L2-only loads (ld.global.cg): the persistent kernel re-reads, step after step, memory
 // that other SMs wrote in the previous step, so nothing may be served from a stale L1 line.
@@ -270,6 +313,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // block-wide exact sum of per-thread fixed-point |u| -> one 128-bit atomic accumulate
 __device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned long long* lo,
                                                  unsigned long long* hi) {
+#if LBM_AV_MODE == 1
+  if (q == 0xffffffffffffffffULL) *lo = q;   // keeps q alive, never true
+  return;
+#endif
   __shared__ unsigned long long warp_sums[32];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
@@ -451,7 +498,7 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
 }
 
 template <typename real, bool STRICT, bool MULTI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LBM_BLOCK_THREADS, (sizeof(real) == 4 ? LBM_MIN_BLOCKS : 1))
 lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   int tx, ty;
   tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
@@ -517,7 +564,7 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
 }
 
 template <typename real, bool STRICT, bool MULTI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LBM_BLOCK_THREADS)
 lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
   int tx, ty;
   tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
@@ -571,7 +618,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, const 
 }
 
 template <typename real, bool STRICT, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LBM_BLOCK_THREADS, (sizeof(real) == 4 ? LBM_PERSIST_MIN_BLOCKS : 1))
 lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
   StepArgs<real> a = pa.s;
   const int pitch = a.pitch;
