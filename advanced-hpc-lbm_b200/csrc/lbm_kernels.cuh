@@ -26,16 +26,16 @@
 // Compile-time tuning knobs of the step kernels (defaults = the measured best, see
 // profiles/r01_kernel_variants.md; tools/build_variants.py builds the alternatives).
 #ifndef LBM_BLOCK_THREADS
-#define LBM_BLOCK_THREADS 256       // threads per block of K1a/K1b/K5
+#define LBM_BLOCK_THREADS 128       // threads per block of K1a/K1b/K5
 #endif
 #ifndef LBM_MIN_BLOCKS
-#define LBM_MIN_BLOCKS 4            // K1a fp32: 4 blocks/SM (64 registers, 56 B spilled) measured +7 %
-#endif                              // over 3 blocks/SM (80 registers): hides the av reduction barrier
+#define LBM_MIN_BLOCKS 7            // K1a fp32: 7 blocks of 128 threads per SM = 72 registers, no spills,
+#endif                              // 896 threads/SM: +8.7 % over 3 x 256 threads at 80 registers
 #ifndef LBM_LOAD_MODE
 #define LBM_LOAD_MODE 0             // 0 plain, 1 ld.global.cs (evict-first), 2 ld.global.nc, 3 nc + L1::no_allocate
 #endif
 #ifndef LBM_PERSIST_MIN_BLOCKS
-#define LBM_PERSIST_MIN_BLOCKS 3    // K5: keeps it at <= 85 registers so 3 blocks/SM are resident
+#define LBM_PERSIST_MIN_BLOCKS 6    // K5: keeps it at <= 85 registers so 6 blocks/SM are resident
 #endif
 #ifndef LBM_AV_MODE
 #define LBM_AV_MODE 0               // 0 block reduction + one atomic per block; 1 = NO av sums (experiment only)

@@ -11,16 +11,9 @@ PKG = os.path.join(ROOT, "advanced-hpc-lbm_b200")
 OUT = os.path.join(PKG, "variants")
 VARIANTS = {
     "base": [],
-    "noav": ["-DLBM_AV_MODE=1"],
-    "mb4": ["-DLBM_MIN_BLOCKS=4"],
-    "mb4_noav": ["-DLBM_MIN_BLOCKS=4", "-DLBM_AV_MODE=1"],
-    "t128": ["-DLBM_BLOCK_THREADS=128"],
-    "t128_mb8": ["-DLBM_BLOCK_THREADS=128", "-DLBM_MIN_BLOCKS=8", "-DLBM_PERSIST_MIN_BLOCKS=6"],
-    "t128_mb8_noav": ["-DLBM_BLOCK_THREADS=128", "-DLBM_MIN_BLOCKS=8", "-DLBM_PERSIST_MIN_BLOCKS=6", "-DLBM_AV_MODE=1"],
-    "t64_mb12": ["-DLBM_BLOCK_THREADS=64", "-DLBM_MIN_BLOCKS=12", "-DLBM_PERSIST_MIN_BLOCKS=12"],
-    "t64_mb16": ["-DLBM_BLOCK_THREADS=64", "-DLBM_MIN_BLOCKS=16", "-DLBM_PERSIST_MIN_BLOCKS=12"],
-    "t128_mb10": ["-DLBM_BLOCK_THREADS=128", "-DLBM_MIN_BLOCKS=10", "-DLBM_PERSIST_MIN_BLOCKS=6"],
-    "mb5": ["-DLBM_MIN_BLOCKS=5"],
+    "t256_mb4": ["-DLBM_BLOCK_THREADS=256", "-DLBM_MIN_BLOCKS=4", "-DLBM_PERSIST_MIN_BLOCKS=3"],
+    "t256_mb3": ["-DLBM_BLOCK_THREADS=256", "-DLBM_MIN_BLOCKS=3", "-DLBM_PERSIST_MIN_BLOCKS=3"],
+    "t128_mb8": ["-DLBM_BLOCK_THREADS=128", "-DLBM_MIN_BLOCKS=8"],
 }
 
 
