@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -47,6 +48,7 @@ struct CudaError {
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+constexpr int kPersistScalarBlocks = 296;      // measured, profiles/r01_small_grids.md
 constexpr size_t kStagingBytes = 64u << 20;   // device staging for AoS<->SoA / mask / fields
 
 // descriptor exchanged between processes (lbm_gpu_ipc_export / _connect)
@@ -105,6 +107,7 @@ struct Slab {
   unsigned long long* up_flag = nullptr;      // neighbour above's kFlagFromBelow
   unsigned long long* dn_flag = nullptr;      // neighbour below's kFlagFromAbove
   void* ipc_mapped[2] = {nullptr, nullptr};   // pointers to close on destroy
+  bool pooled = false;                        // base/staging came from the stream-ordered pool
 };
 
 template <typename real> struct ParamT;
@@ -138,16 +141,48 @@ class Grid : public GridBase {
       if (s.stream) cudaStreamSynchronize(s.stream);
       for (int i = 0; i < 2; i++)
         if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
+      if (s.av_lo) cudaFree(s.av_lo);
+      if (s.win) cudaFree(s.win);
+      pool_free(s.staging, s);
+      pool_free(s.base, s);
+      if (s.stream) cudaStreamSynchronize(s.stream);
       if (s.ev0) cudaEventDestroy(s.ev0);
       if (s.ev1) cudaEventDestroy(s.ev1);
       for (int i = 0; i < 2; i++)
         if (s.step_ev[i]) cudaEventDestroy(s.step_ev[i]);
       if (s.stream) cudaStreamDestroy(s.stream);
-      if (s.av_lo) cudaFree(s.av_lo);
-      if (s.staging) cudaFree(s.staging);
-      if (s.win) cudaFree(s.win);
-      if (s.base) cudaFree(s.base);
     }
+  }
+
+  // The lattice and the staging buffer come from the device's stream-ordered memory pool
+  // with an unlimited release threshold: destroying a lattice and creating the next one of
+  // a similar size (parameter sweeps, bench.py's end-to-end leg) reuses the pages instead
+  // of paying cudaFree + cudaMalloc of ~20 GB each time.  LBM_GPU_NO_POOL=1 switches to
+  // plain cudaMalloc/cudaFree.  The halo window is always a plain allocation (CUDA IPC).
+  static bool use_pool() {
+    const char* e = getenv("LBM_GPU_NO_POOL");
+    return !(e && e[0] && e[0] != '0');
+  }
+  void pool_alloc(void** p, size_t bytes, Slab<real>& s) {
+    if (use_pool()) {
+      int supported = 0;
+      CK(cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, s.device));
+      if (supported) {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, s.device));
+        unsigned long long keep = ~0ULL;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        CK(cudaMallocAsync(p, bytes, s.stream));
+        s.pooled = true;
+        return;
+      }
+    }
+    CK(cudaMalloc(p, bytes));
+  }
+  static void pool_free(void* p, Slab<real>& s) {
+    if (!p) return;
+    if (s.pooled) cudaFreeAsync(p, s.stream);
+    else cudaFree(p);
   }
 
   // ---------------------------------------------------------------- allocation ----
@@ -162,7 +197,8 @@ class Grid : public GridBase {
     for (int i = 0; i < 2; i++) { s.off_side[i] = off; off = round_up(off + side, 256); }
     s.off_mask = off; off = round_up(off + maskb, 256);
     s.bytes = off;
-    CK(cudaMalloc((void**)&s.base, s.bytes));
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    pool_alloc((void**)&s.base, s.bytes, s);
     for (int i = 0; i < 2; i++) {
       s.lattice[i] = (real*)(s.base + s.off_lattice[i]);
       s.side[i] = (real*)(s.base + s.off_side[i]);
@@ -174,13 +210,14 @@ class Grid : public GridBase {
     s.win_bytes = round_up(s.off_sync + kSyncWords * sizeof(unsigned long long), 2u << 20);
     CK(cudaMalloc((void**)&s.win, s.win_bytes));
     s.sync = (unsigned long long*)(s.win + s.off_sync);
-    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s.ev0));
     CK(cudaEventCreate(&s.ev1));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&s.step_ev[i], cudaEventDisableTiming));
     CK(cudaMemsetAsync(s.base + s.off_side[0], 0, s.bytes - s.off_side[0], s.stream));
     CK(cudaMemsetAsync(s.win, 0, s.win_bytes, s.stream));
-    CK(cudaMalloc(&s.staging, kStagingBytes));
+    void* st = nullptr;
+    pool_alloc(&st, kStagingBytes, s);
+    s.staging = st;
   }
 
   // window section: parity b, direction d (0 = "from below": speeds 2,5,6; 1 = "from above": 4,7,8)
@@ -240,10 +277,13 @@ class Grid : public GridBase {
       tile_shape(vec, bx, by);
       return (long long)((prm.nx / vec + bx - 1) / bx) * ((slabs[0].rows + by - 1) / by);
     };
-    // tiny grids: one cell per thread if all of those tiles can be resident at once
+    // tiny grids: one cell per thread (4x the threads on the step's dependent-latency chain)
+    // as long as that does not put more than kPersistScalarBlocks blocks on the grid barrier
     long long tiles = tiles_for(1);
     int cap = persistent_capacity(slabs[0]);
-    if (tiles > cap && prm.nx % 4 == 0) {
+    long long scalar_limit = std::min<long long>(cap, kPersistScalarBlocks);
+    if (const char* e = getenv("LBM_PERSIST_VEC")) scalar_limit = (atoi(e) == 1) ? cap : 0;   // experiments
+    if (tiles > scalar_limit && prm.nx % 4 == 0) {
       tiles = tiles_for(4);
       cap = persistent_capacity(slabs[0]);
     }

@@ -4,6 +4,7 @@
 
 #include <ctype.h>
 #include <errno.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -113,23 +114,140 @@ uint32_t* lbm_read_obstacle_bits(const char* obstaclefile, int nx, int ny)
   return bits;
 }
 
+/* ---------------------------------------------------------------------------------
+ * Fast, exact "%.12E".  The output files are millions of lines of four such numbers;
+ * once the step loop runs on the GPU, fprintf's general-purpose conversion is what the
+ * program spends its time in.  v = m * 2^e exactly, so
+ * v * 10^p = m * 5^p * 2^(e+p) is an integer shift away from a 128-bit product; rounding
+ * half-to-even on that exact value gives the same 13 digits glibc prints.  Values outside
+ * the range the 128-bit product covers fall back to snprintf.
+ * tests/test_host_format.py compares it with printf on millions of values.
+ * --------------------------------------------------------------------------------- */
+typedef unsigned __int128 u128;
+
+static u128 pow5_table[56];
+static int pow5_ready = 0;
+
+static void pow5_init(void)
+{
+  pow5_table[0] = 1;
+  for (int i = 1; i < 56; i++) pow5_table[i] = pow5_table[i - 1] * 5;
+  pow5_ready = 1;
+}
+
+int lbm_format_e12(char* out, double v)
+{
+  union { double d; uint64_t u; } x;
+  x.d = v;
+  const int neg = (int)(x.u >> 63);
+  const uint64_t frac = x.u & ((1ULL << 52) - 1);
+  const int be = (int)((x.u >> 52) & 0x7ff);
+  if (be == 0x7ff) return sprintf(out, "%.12E", v);
+  char* o = out;
+  if (neg) *o++ = '-';
+  if (be == 0 && frac == 0) {
+    memcpy(o, "0.000000000000E+00", 18);
+    o += 18;
+    *o = '\0';
+    return (int)(o - out);
+  }
+  if (!pow5_ready) pow5_init();
+  uint64_t m = (be == 0) ? frac : (frac | (1ULL << 52));
+  int e = (be == 0) ? -1074 : be - 1075;
+  const int tz = __builtin_ctzll(m);
+  m >>= tz;
+  e += tz;
+  const int bl = 64 - __builtin_clzll(m);
+  int k = (int)floor((double)(e + bl - 1) * 0.30102999566398120);
+  const uint64_t lo_lim = 1000000000000ULL, hi_lim = 10000000000000ULL;
+  uint64_t n = 0;
+  for (int tries = 0; ; tries++) {
+    const int p = 12 - k;
+    if (tries > 3 || p < 0 || p > 55) return sprintf(out, "%.12E", v);
+    /* bits of m * 5^p: bl + ceil(p * log2(5)) */
+    const int need = bl + (int)(p * 2.3219280948873623) + 1;
+    if (need > 126) return sprintf(out, "%.12E", v);
+    const u128 a = (u128)m * pow5_table[p];
+    const int sh = e + p;
+    u128 q;
+    if (sh >= 0) {
+      if (need + sh > 126) return sprintf(out, "%.12E", v);
+      q = a << sh;
+    } else {
+      const int s = -sh;
+      if (s >= 127) return sprintf(out, "%.12E", v);
+      q = a >> s;
+      const u128 rem = a & (((u128)1 << s) - 1);
+      const u128 half = (u128)1 << (s - 1);
+      if (rem > half || (rem == half && (q & 1))) q++;
+    }
+    if (q < lo_lim) { k--; continue; }
+    if (q >= hi_lim) { k++; continue; }
+    n = (uint64_t)q;
+    break;
+  }
+  char digits[13];
+  for (int i = 12; i >= 0; i--) { digits[i] = (char)('0' + n % 10); n /= 10; }
+  *o++ = digits[0];
+  *o++ = '.';
+  memcpy(o, digits + 1, 12);
+  o += 12;
+  *o++ = 'E';
+  int ex = k;
+  if (ex < 0) { *o++ = '-'; ex = -ex; } else { *o++ = '+'; }
+  if (ex >= 100) { *o++ = (char)('0' + ex / 100); ex %= 100; }
+  *o++ = (char)('0' + ex / 10);
+  *o++ = (char)('0' + ex % 10);
+  *o = '\0';
+  return (int)(o - out);
+}
+
+static char* put_int(char* o, long long v)
+{
+  char tmp[24];
+  int n = 0;
+  if (v < 0) { *o++ = '-'; v = -v; }
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) *o++ = tmp[--n];
+  return o;
+}
+
 void lbm_write_final_state_rows(void* fpv, int nx, long long row0, long long nrows,
                                 const double* u_x, const double* u_y, const double* u,
                                 const double* pressure, const uint32_t* obstacle_bits)
 {
   FILE* fp = (FILE*)fpv;
+  enum { LINE_MAX_BYTES = 160, CHUNK = 4096 };
+  char* buf = (char*)malloc((size_t)CHUNK * LINE_MAX_BYTES);
+  if (buf == NULL) die("cannot allocate memory for output rows", __LINE__, __FILE__);
+  char* o = buf;
+  int lines = 0;
   for (long long r = 0; r < nrows; r++) {
     const long long jj = row0 + r;
     for (int ii = 0; ii < nx; ii++) {
       const size_t n = (size_t)r * (size_t)nx + (size_t)ii;
-      /* last column: the cell's own obstacle flag.  The reference prints
-       * obstacles[ii*nx + jj] (d2q9-bgk.c:2978), a transposed index that differs from
-       * the golden files in check/ for non-symmetric masks; the golden files hold the
-       * cell's own flag, which is what is written here (check.py ignores the column). */
-      fprintf(fp, "%d %lld %.12E %.12E %.12E %.12E %d\n", ii, jj, u_x[n], u_y[n], u[n], pressure[n],
-              lbm_obstacle_bit(obstacle_bits, nx, ii, (int)jj));
+      /* "%d %d %.12E %.12E %.12E %.12E %d\n" (d2q9-bgk.c:2978).  Last column: the cell's
+       * own obstacle flag.  The reference prints obstacles[ii*nx + jj], a transposed index
+       * that differs from the golden files in check/ for non-symmetric masks; the golden
+       * files hold the cell's own flag, which is what is written here (check.py ignores
+       * the column). */
+      o = put_int(o, ii); *o++ = ' ';
+      o = put_int(o, jj); *o++ = ' ';
+      o += lbm_format_e12(o, u_x[n]); *o++ = ' ';
+      o += lbm_format_e12(o, u_y[n]); *o++ = ' ';
+      o += lbm_format_e12(o, u[n]); *o++ = ' ';
+      o += lbm_format_e12(o, pressure[n]); *o++ = ' ';
+      *o++ = (char)('0' + lbm_obstacle_bit(obstacle_bits, nx, ii, (int)jj));
+      *o++ = '\n';
+      if (++lines == CHUNK) {
+        if (fwrite(buf, 1, (size_t)(o - buf), fp) != (size_t)(o - buf)) die("could not write output file", __LINE__, __FILE__);
+        o = buf;
+        lines = 0;
+      }
     }
   }
+  if (o != buf && fwrite(buf, 1, (size_t)(o - buf), fp) != (size_t)(o - buf)) die("could not write output file", __LINE__, __FILE__);
+  free(buf);
 }
 
 void lbm_write_av_vels(const char* path, int n, const double* av_vels)
@@ -138,6 +256,14 @@ void lbm_write_av_vels(const char* path, int n, const double* av_vels)
   if (fp == NULL) die("could not open file output file", __LINE__, __FILE__);
   static char big[1 << 20];
   setvbuf(fp, big, _IOFBF, sizeof big);
-  for (int ii = 0; ii < n; ii++) fprintf(fp, "%d:\t%.12E\n", ii, av_vels[ii]);
+  char line[64];
+  for (int ii = 0; ii < n; ii++) {
+    /* "%d:\t%.12E\n" (d2q9-bgk.c:2993) */
+    char* o = put_int(line, ii);
+    *o++ = ':'; *o++ = '\t';
+    o += lbm_format_e12(o, av_vels[ii]);
+    *o++ = '\n';
+    fwrite(line, 1, (size_t)(o - line), fp);
+  }
   fclose(fp);
 }

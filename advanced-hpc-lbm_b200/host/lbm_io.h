@@ -35,4 +35,7 @@ void lbm_write_final_state_rows(void* fp, int nx, long long row0, long long nrow
 
 void lbm_write_av_vels(const char* path, int n, const double* av_vels);
 
+/* exact equivalent of sprintf(out, "%.12E", v); returns the number of characters */
+int lbm_format_e12(char* out, double v);
+
 #endif

@@ -1,0 +1,54 @@
+"""advanced-hpc-lbm_b200/host/lbm_io.c: the hand-written "%.12E" conversion used by the
+output writers must be byte-identical to printf's on every value (the file contract is
+d2q9-bgk.c:2978 and :2993)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "advanced-hpc-lbm_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def io_lib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("io") / "liblbm_io_test.so")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + HOST, os.path.join(HOST, "lbm_io.c"), "-lm", "-o", so])
+    lib = C.CDLL(so)
+    lib.lbm_format_e12.argtypes = [C.c_char_p, C.c_double]
+    lib.lbm_format_e12.restype = C.c_int
+    return lib
+
+
+def fmt(lib, v):
+    buf = C.create_string_buffer(64)
+    n = lib.lbm_format_e12(buf, v)
+    s = buf.value.decode()
+    assert n == len(s)
+    return s
+
+
+def test_special_and_edge_values(io_lib):
+    vals = [0.0, -0.0, 1.0, -1.0, 10.0, 9.9999999999995, 9.99999999999949, 0.1, 1e-5, 123456789012.5,
+            1234567890123.5, 1e12, 1e13, 9.999999999999e12, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+            float(np.float32(0.1)), float(np.float32(1) / np.float32(3)) * 0.1, 3.333333507180e-02,
+            0.5 ** 60, 1 - 2 ** -53, 1.0000000000005, 1.00000000000050004, 2.5e-13 + 1, 1e-32, 1e-40,
+            float("inf"), float("-inf")]
+    for v in vals:
+        assert fmt(io_lib, v) == ("%.12E" % v).replace("INF", "INF"), repr(v)
+    assert fmt(io_lib, float("nan")).upper().lstrip("-") == "NAN"
+
+
+def test_matches_printf_on_random_floats_and_doubles(io_lib):
+    rng = np.random.default_rng(12345)
+    # the values the program prints: fp32 promoted to double, magnitudes 1e-12 .. 1
+    f32 = (10.0 ** rng.uniform(-12, 0.5, 300000) * rng.choice([-1.0, 1.0], 300000)).astype(np.float32)
+    f64 = 10.0 ** rng.uniform(-25, 12.9, 200000)
+    bits = rng.integers(0, 2 ** 63 - 1, 50000, dtype=np.int64).view(np.float64)      # any finite double
+    ties = (rng.integers(10 ** 12, 10 ** 13, 20000).astype(np.float64) + 0.5) / 1e3  # near half-way cases
+    for arr in (f32.astype(np.float64), f64, bits[np.isfinite(bits)], ties):
+        for v in arr.tolist():
+            assert fmt(io_lib, v) == "%.12E" % v, repr(v)
