@@ -23,6 +23,7 @@ KERNEL_TMA = 8
 KERNEL_VEC4 = 16
 SYNC_FLAGS = 32
 KERNEL_PERSISTENT = 64
+POOL = 128
 IPC_DESC_BYTES = 256
 
 
@@ -75,6 +76,7 @@ SYMBOLS = {
     "lbm_gpu_download_f64": (C.c_int, [_P, _P]),
     "lbm_gpu_final_fields_f64": (C.c_int, [_P, C.c_longlong, C.c_longlong, _P, _P, _P, _P]),
     "lbm_gpu_av_velocity_f64": (C.c_int, [_P, _P]),
+    "lbm_gpu_digest": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "lbm_gpu_upload": (C.c_int, [_P, _P]),
     "lbm_gpu_upload_f64": (C.c_int, [_P, _P]),
     "lbm_gpu_get_info": (C.c_int, [_P, C.POINTER(Info)]),
@@ -123,6 +125,20 @@ def pack_obstacle_bits(obstacles):
     padded[:, :nx] = m
     bits = np.packbits(padded.reshape(ny, wpr, 32), axis=-1, bitorder="little")
     return np.ascontiguousarray(bits).view(np.uint32).reshape(ny, wpr)
+
+
+def lattice_checksum(cells, global_row0=0):
+    """numpy restatement of the device checksum (csrc/lbm_kernels.cuh, lbm_digest) for an
+    AoS lattice (rows, nx, 9) of float32 or float64."""
+    cells = np.ascontiguousarray(cells)
+    rows, nx, _ = cells.shape
+    bits = cells.view(np.uint32 if cells.dtype == np.float32 else np.uint64).astype(np.uint64)
+    g = (np.arange(rows, dtype=np.uint64)[:, None] + np.uint64(global_row0)) * np.uint64(nx) \
+        + np.arange(nx, dtype=np.uint64)[None, :]
+    k = np.arange(1, 10, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        w = (g[:, :, None] * np.uint64(0x9E3779B97F4A7C15) + k[None, None, :] * np.uint64(0xC2B2AE3D27D4EB4F)) | np.uint64(1)
+        return int(np.sum(bits * w, dtype=np.uint64))
 
 
 class PinnedArray:
@@ -264,6 +280,12 @@ class Lattice:
             v = C.c_float()
             _check(self.lib.lbm_gpu_av_velocity(self.h, C.byref(v)))
         return v.value
+
+    def digest(self):
+        """(total_density, checksum) of the local rows: exact, additive over ranks."""
+        d, c = C.c_double(), C.c_ulonglong()
+        _check(self.lib.lbm_gpu_digest(self.h, C.byref(d), C.byref(c)))
+        return d.value, c.value
 
     def info(self):
         i = Info()

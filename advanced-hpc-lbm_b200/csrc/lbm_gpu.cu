@@ -6,6 +6,7 @@
 #include "lbm_gpu.h"
 #include "lbm_kernels.cuh"
 
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -136,33 +137,42 @@ class Grid : public GridBase {
   bool is_f64() const override { return sizeof(real) == 8; }
 
   ~Grid() override {
+    const bool dbg = getenv("LBM_GPU_DEBUG_TIMING") != nullptr;
+    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
     for (auto& s : slabs) {
+      double t0 = now();
       cudaSetDevice(s.device);
       if (s.stream) cudaStreamSynchronize(s.stream);
+      double t1 = now();
       for (int i = 0; i < 2; i++)
         if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
-      if (s.av_lo) cudaFree(s.av_lo);
-      if (s.win) cudaFree(s.win);
+      double t2 = now();
       pool_free(s.staging, s);
       pool_free(s.base, s);
       if (s.stream) cudaStreamSynchronize(s.stream);
+      double t3 = now();
+      if (s.av_lo) cudaFree(s.av_lo);
+      if (s.win) cudaFree(s.win);
+      double t4 = now();
       if (s.ev0) cudaEventDestroy(s.ev0);
       if (s.ev1) cudaEventDestroy(s.ev1);
       for (int i = 0; i < 2; i++)
         if (s.step_ev[i]) cudaEventDestroy(s.step_ev[i]);
       if (s.stream) cudaStreamDestroy(s.stream);
+      double t5 = now();
+      if (dbg) fprintf(stderr, "[lbm destroy] sync %.2f ipc-close %.2f pool-free %.2f cudaFree(small) %.2f events/stream %.2f ms\n",
+                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
     }
   }
 
-  // The lattice and the staging buffer come from the device's stream-ordered memory pool
-  // with an unlimited release threshold: destroying a lattice and creating the next one of
-  // a similar size (parameter sweeps, bench.py's end-to-end leg) reuses the pages instead
-  // of paying cudaFree + cudaMalloc of ~20 GB each time.  LBM_GPU_NO_POOL=1 switches to
-  // plain cudaMalloc/cudaFree.  The halo window is always a plain allocation (CUDA IPC).
-  static bool use_pool() {
-    const char* e = getenv("LBM_GPU_NO_POOL");
-    return !(e && e[0] && e[0] != '0');
-  }
+  // LBM_GPU_POOL: the lattice and the staging buffer come from the device's stream-ordered
+  // memory pool with an unlimited release threshold, so destroying a lattice and creating
+  // the next one of a similar size (parameter sweeps, bench.py's end-to-end leg) reuses
+  // the pages instead of paying cudaFree + cudaMalloc of ~20 GB each time (25-80 ms).
+  // Not the default: the pool's first growth is slower than one cudaMalloc (0.4 s for
+  // 19 GB), which a one-shot CLI run would pay for nothing, and the memory stays with the
+  // process after lbm_gpu_destroy.  The halo window is always a plain allocation (CUDA IPC).
+  bool use_pool() const { return (flags & LBM_GPU_POOL) != 0; }
   void pool_alloc(void** p, size_t bytes, Slab<real>& s) {
     if (use_pool()) {
       int supported = 0;
@@ -644,6 +654,29 @@ class Grid : public GridBase {
     }
     return (double)((long double)tot / (long double)LBM_FIX_SCALE);
   }
+
+  // exact digest of the rows held by this process (see lbm_digest)
+  void digest(double* total_density, unsigned long long* checksum) {
+    const int cur = (int)(steps_done & 1);
+    unsigned long long mass = 0, sum = 0;
+    for (auto& s : slabs) {
+      CK(cudaSetDevice(s.device));
+      unsigned long long* out = s.sync + kScratch1;
+      CK(cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), s.stream));
+      const long long ncells = (long long)s.rows * prm.nx;
+      lbm::lbm_digest<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
+          s.lattice[cur], plane_stride(s), pitch, prm.nx, 0, s.rows, s.row0, out);
+      CK(cudaGetLastError());
+      launches++;
+      unsigned long long w[2];
+      CK(cudaMemcpyAsync(w, out, sizeof w, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+      mass += w[0];
+      sum += w[1];
+    }
+    if (total_density) *total_density = (double)(long long)mass / 4294967296.0;
+    if (checksum) *checksum = sum;
+  }
 };
 
 // split ny rows over n slabs: remainder spread over the first slabs
@@ -943,6 +976,13 @@ int lbm_gpu_av_velocity_f64(lbm_gpu* h, double* av_out) {
   return guarded<double>(h, "lbm_gpu_av_velocity_f64", [&](Grid<double>& g) {
     *av_out = g.av_velocity_sum() / (double)g.divisor();
   });
+}
+
+int lbm_gpu_digest(lbm_gpu* h, double* total_density, unsigned long long* checksum) {
+  if (!h) return fail("lbm_gpu_digest: NULL handle");
+  if (reinterpret_cast<GridBase*>(h)->is_f64())
+    return guarded<double>(h, "lbm_gpu_digest", [&](Grid<double>& g) { g.digest(total_density, checksum); });
+  return guarded<float>(h, "lbm_gpu_digest", [&](Grid<float>& g) { g.digest(total_density, checksum); });
 }
 
 int lbm_gpu_upload(lbm_gpu* h, const float* cells_aos) {

@@ -802,4 +802,42 @@ __global__ void lbm_fields(const real* __restrict__ buf, const uint32_t* __restr
   if (av_lo) block_accumulate(q, av_lo, av_hi);
 }
 
+// Digest of the lattice rows [r0, r0+nrows): two wrapping 64-bit integer sums, so they
+// are exact, order-independent and additive over slabs / ranks.
+//   mass      sum over cells and speeds of round(f * 2^32): total_density of the reference
+//             (d2q9-bgk.c:2900-2916) in fixed point -- stays constant step after step;
+//   checksum  sum of bit_pattern(f_k(cell)) * odd_weight(global cell index, k): equal for
+//             two lattices iff (up to 2^-64) every speed of every cell has the same bits,
+//             whatever the decomposition.  Full-size stand-in for a lattice comparison.
+__device__ __forceinline__ unsigned long long bits_of(float f) { return (unsigned long long)__float_as_uint(f); }
+__device__ __forceinline__ unsigned long long bits_of(double f) { return (unsigned long long)__double_as_longlong(f); }
+
+template <typename real>
+__global__ void lbm_digest(const real* __restrict__ buf, long long plane_stride, int pitch, int nx, int r0,
+                           int nrows, long long global_row0, unsigned long long* out /* [mass, checksum] */) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mass = 0ULL, sum = 0ULL;
+  if (n < (long long)nrows * nx) {
+    const int row = (int)(n / nx);
+    const int x = (int)(n - (long long)row * nx);
+    const unsigned long long g = (unsigned long long)(global_row0 + row) * (unsigned long long)nx + (unsigned long long)x;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const real f = buf[k * plane_stride + (long long)(r0 + row) * pitch + x];
+      mass += (unsigned long long)__double2ll_rn((double)f * 4294967296.0);
+      const unsigned long long w = (g * 0x9E3779B97F4A7C15ULL + (unsigned long long)(k + 1) * 0xC2B2AE3D27D4EB4FULL) | 1ULL;
+      sum += bits_of(f) * w;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mass += __shfl_down_sync(0xffffffffu, mass, off);
+    sum += __shfl_down_sync(0xffffffffu, sum, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mass) atomicAdd(out + 0, mass);
+    if (sum) atomicAdd(out + 1, sum);
+  }
+}
+
 }  // namespace lbm

@@ -296,10 +296,11 @@ def main():
     global_free = sum_over_ranks(float((pin_obst.array == 0).sum()))
 
     def make_lattice():
+        # LBM_GPU_POOL: device memory of a destroyed lattice is reused by the next create
         if world == 1:
-            return L.Lattice(NX, ny, DENSITY, ACCEL, OMEGA, obstacles=pin_obst.array)
+            return L.Lattice(NX, ny, DENSITY, ACCEL, OMEGA, obstacles=pin_obst.array, flags=L.POOL)
         lat = L.Lattice(NX, ny, DENSITY, ACCEL, OMEGA, obstacles=pin_obst.array, slab=(row0, nrows),
-                        device_ids=[local_rank])
+                        device_ids=[local_rank], flags=L.POOL)
         below, above = slabs.exchange_descriptors(lat.ipc_export(), rank, world, dist)
         lat.ipc_connect(below, above)
         barrier()
@@ -362,7 +363,7 @@ def main():
                "h2d_bytes_per_step": int(pin_obst.array.nbytes) * world,
                "d2h_bytes_per_step": int(4 * out[0].array.nbytes + av_host.nbytes) * world,
                "ms_per_step": 1e3 * e2e_s / K,
-               "what": "lbm_gpu_create(int32 obstacles from pinned host) + lbm_gpu_run(T) -> av_vels on host + "
+               "what": "lbm_gpu_create(LBM_GPU_POOL, int32 obstacles from pinned host) + lbm_gpu_run(T) -> av_vels on host + "
                        "lbm_gpu_final_fields(u_x,u_y,|u|,pressure) -> pinned host + lbm_gpu_destroy"}
         for o in out:
             o.free()

@@ -68,6 +68,9 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
 #define LBM_GPU_KERNEL_PERSISTENT 64u /* force the persistent cooperative kernel (all steps of a run
                                       in one launch; single GPU, nx % 4 == 0).  Chosen by default
                                       for grids small enough to live in L2 */
+#define LBM_GPU_POOL         128u  /* take the lattice from the device's stream-ordered memory pool and
+                                      leave it there on destroy: a host that creates many lattices in
+                                      one process (sweeps) skips cudaMalloc/cudaFree of ~20 GB each time */
 #define LBM_GPU_SYNC_FLAGS    32u  /* lbm_gpu_create with n_gpus > 1: order the slabs with the
                                       device-side flag protocol of the one-process-per-GPU form
                                       instead of CUDA events (every slab on its own GPU) */
@@ -175,6 +178,17 @@ int lbm_gpu_download_f64(lbm_gpu* h, double* cells_aos_out);
 int lbm_gpu_final_fields_f64(lbm_gpu* h, long long row0, long long nrows,
                              double* u_x, double* u_y, double* u, double* pressure);
 int lbm_gpu_av_velocity_f64(lbm_gpu* h, double* av_out);
+
+/*
+ * Exact digest of the rows held by this process, computed on the device:
+ *   total_density  the reference's total_density() (d2q9-bgk.c:2900-2916; its -DDEBUG mass
+ *                  conservation check), summed in 2^-32 fixed point;
+ *   checksum       wrapping 64-bit sum of bit_pattern(speed) * odd_weight(global cell, k).
+ * Both are integer sums: independent of summation order and additive over slabs and
+ * ranks, so two runs hold the same lattice iff their checksums agree -- the way to
+ * compare lattices too large to download (16384 x 131072 is 77 GB).  Either may be NULL.
+ */
+int lbm_gpu_digest(lbm_gpu* h, double* total_density, unsigned long long* checksum);
 
 /* Replace the device lattice by the caller's (whole local rows, AoS). */
 int lbm_gpu_upload(lbm_gpu* h, const float* cells_aos);
