@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -555,13 +556,18 @@ class Grid : public GridBase {
     if (sums_out) {
       std::vector<unsigned long long> lo(n_steps), hi(n_steps);
       std::vector<unsigned __int128> tot(n_steps, 0);
+      std::vector<char> bad(n_steps, 0);
       for (auto& s : slabs) {
         CK(cudaSetDevice(s.device));
         CK(cudaMemcpy(lo.data(), s.av_lo, n_steps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hi.data(), s.av_hi, n_steps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (int t = 0; t < n_steps; t++) tot[t] += ((unsigned __int128)hi[t] << 64) | lo[t];
+        for (int t = 0; t < n_steps; t++) {
+          if (hi[t] & LBM_NONFINITE_MARK) bad[t] = 1;
+          tot[t] += ((unsigned __int128)(hi[t] & ~LBM_NONFINITE_MARK) << 64) | lo[t];
+        }
       }
-      for (int t = 0; t < n_steps; t++) sums_out[t] = (double)((long double)tot[t] / (long double)LBM_FIX_SCALE);
+      for (int t = 0; t < n_steps; t++)
+        sums_out[t] = bad[t] ? std::nan("") : (double)((long double)tot[t] / (long double)LBM_FIX_SCALE);
     }
   }
 

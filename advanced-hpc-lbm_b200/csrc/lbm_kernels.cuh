@@ -87,6 +87,11 @@ template <> struct Ops<double, false> {
 // are associative, so the per-step average does not depend on block scheduling, grid
 // shape or on how the rows are split over GPUs.
 #define LBM_FIX_SCALE 4503599627370496.0 /* 2^52 */
+// A cell whose |u| is NaN or beyond any physical value (the lattice has blown up) cannot
+// be represented in the fixed-point sum: the step's high word gets this bit and the host
+// reports that step's average as NaN, which is what the reference's float sum would give.
+#define LBM_SPEED_LIMIT 2048.0
+#define LBM_NONFINITE_MARK (1ULL << 63)
 __device__ __forceinline__ unsigned long long to_fixed(float s) {
   return __float2ull_rn(s * 4503599627370496.0f);
 }
@@ -451,6 +456,7 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
   for (int j = 0; j < 4; j++) {
     const real s = cell_update<real, STRICT>(in[j], (mbits >> j) & 1u, a.omega, out[j]);
     q += to_fixed(s);
+    if (active && !(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);   // NaN / blow-up
   }
 
   if (active) {
@@ -540,6 +546,7 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
     const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
     const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
     q = to_fixed(s);
+    if (!(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);
 #pragma unroll
     for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
     if (cA) {
@@ -632,13 +639,15 @@ lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
     a.halo_n = pa.window + (size_t)((src * 2 + 1) * 3) * pitch;
     a.push_up = pa.window + (size_t)((dst * 2 + 0) * 3) * pitch;
     a.push_dn = pa.window + (size_t)((dst * 2 + 1) * 3) * pitch;
+    a.av_lo = pa.av_lo + t;
+    a.av_hi = pa.av_hi + t;
     unsigned long long q = 0ULL;
     for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
       const int ty = tile / a.tiles_x;
       const int tx = tile - ty * a.tiles_x;
       q += (VEC == 4) ? vec4_tile<real, STRICT, true>(a, tx, ty) : scalar_tile<real, STRICT, true>(a, tx, ty);
     }
-    block_accumulate(q, pa.av_lo + t, pa.av_hi + t);
+    block_accumulate(q, a.av_lo, a.av_hi);
     grid_barrier(pa.barrier, (unsigned long long)gridDim.x * (unsigned long long)(t + 1));
   }
 }

@@ -174,6 +174,24 @@ def test_mass_is_conserved_over_many_steps():
     assert np.all(np.isfinite(av)) and np.all(av > 0)
 
 
+def test_blown_up_lattice_reports_nan_like_the_reference():
+    """A lattice with a zero-density cell makes the reference's float sum NaN from that step
+    on (0/0 in the velocity); the exact integer sum cannot hold NaN, so the kernel marks
+    the step instead and the host reports NaN -- check.py then fails the run as it would
+    fail the reference's."""
+    nx, ny = 64, 8
+    cells, obst = O.random_lattice(nx, ny, seed=6, p_obst=0.0, walls=False)
+    obst[:] = 0
+    cells[3, 10, :] = 0.0
+    cells[2:5, 9:12, :] = 0.0            # a hole of zero density: pulled values are all zero
+    for k in (L.KERNEL_VEC4, L.KERNEL_SCALAR, L.KERNEL_PERSISTENT):
+        with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
+            av = lat.run(3)
+        assert np.isnan(av[0]), (k, av)
+    _, av_ref, _ = O.run(cells, obst, 1, DENSITY, ACCEL, OMEGA)
+    assert np.isnan(av_ref[0])
+
+
 def test_errors_are_reported_not_fatal():
     with pytest.raises(L.LbmError, match="ny >= 2"):
         L.Lattice(8, 1, DENSITY, ACCEL, OMEGA)
