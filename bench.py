@@ -208,7 +208,7 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "MLUPS (d2q9-bgk lattice updates per second / 1e6)",
         "value": value, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_time / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * tot_time / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
         "cpu_baseline": info,
@@ -220,9 +220,10 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(args, world):
+    ny = ROWS_PER_GPU * world if args.scaling == "weak" else ROWS_PER_GPU
     return {"workload": "synthetic %dx%d channel (walls rows 0 and ny-1, Bernoulli 1%% obstacles, seed 20240229), "
-                        "%d rows per GPU" % (NX, ROWS_PER_GPU * world, ROWS_PER_GPU),
-            "nx": NX, "ny": ROWS_PER_GPU * world, "timesteps_per_step": args.timesteps,
+                        "%d rows per GPU" % (NX, ny, ny // world),
+            "nx": NX, "ny": ny, "timesteps_per_step": args.timesteps,
             "density": DENSITY, "accel": ACCEL, "omega": OMEGA,
             "l2": "inputs larger than L2 (19.3 GB lattice per GPU vs 126 MB), no flush needed",
             "parallelism": "row slabs, %d GPU(s), halo rows pushed by the step kernel over NVLink" % world}
@@ -236,6 +237,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--timesteps", type=int, default=200, help="lattice timesteps per bench step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 16384 rows per GPU (default, the contract); strong: 16384 rows in total "
+                         "(BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -284,7 +288,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ny = ROWS_PER_GPU * world
+    ny = ROWS_PER_GPU * world if args.scaling == "weak" else ROWS_PER_GPU
     row0, nrows = L.split_rows(ny, world)[rank]
     T, K, W = args.timesteps, args.steps, args.warmup
     cells_total = float(NX) * float(ny)
@@ -385,7 +389,7 @@ def main():
     line = {
         "metric": "MLUPS (d2q9-bgk lattice updates per second / 1e6)",
         "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
         "achieved_hbm_gbs_per_gpu": achieved,
