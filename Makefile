@@ -30,7 +30,7 @@ $(EXE): $(PKG)/host/d2q9-bgk.c $(PKG)/host/lbm_io.c $(PKG)/host/lbm_io.h include
 check/%.av_vels.dat check/%.final_state.dat:
 	python tests/golden/expand_golden.py check
 
-check:
+check: $(REF_AV_VELS_FILE) $(REF_FINAL_STATE_FILE)
 	python check/check.py --ref-av-vels-file=$(REF_AV_VELS_FILE) --ref-final-state-file=$(REF_FINAL_STATE_FILE) --av-vels-file=$(AV_VELS_FILE) --final-state-file=$(FINAL_STATE_FILE)
 
 oracle:
