@@ -192,6 +192,27 @@ def test_blown_up_lattice_reports_nan_like_the_reference():
     assert np.isnan(av_ref[0])
 
 
+def test_degenerate_masks():
+    """No obstacle file at all (obstacles=NULL), and a grid that is all obstacles: the
+    reference divides by tot_cells = 0 there (d2q9-bgk.c:1811) and gets NaN; so do we."""
+    nx, ny = 64, 6
+    cells, _ = O.random_lattice(nx, ny, seed=12)
+    none = np.zeros((ny, nx), dtype=np.int32)
+    ref, _, av_ref = O.run(cells, none, 4, DENSITY, ACCEL, OMEGA)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=None, flags=L.STRICT) as lat:
+        av = lat.run(4)
+        assert np.array_equal(lat.download(), ref)
+        assert lat.info().free_cells == nx * ny
+    np.testing.assert_allclose(av, av_ref, rtol=1e-6)
+    full = np.ones((ny, nx), dtype=np.int32)
+    ref, _, _ = O.run(cells, full, 3, DENSITY, ACCEL, OMEGA)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=full, flags=L.STRICT) as lat:
+        av = lat.run(3)
+        assert np.array_equal(lat.download(), ref)          # pure bounce-back everywhere
+        assert lat.info().free_cells == 0
+    assert np.all(np.isnan(av))
+
+
 def test_errors_are_reported_not_fatal():
     with pytest.raises(L.LbmError, match="ny >= 2"):
         L.Lattice(8, 1, DENSITY, ACCEL, OMEGA)

@@ -52,3 +52,46 @@ def test_matches_printf_on_random_floats_and_doubles(io_lib):
     for arr in (f32.astype(np.float64), f64, bits[np.isfinite(bits)], ties):
         for v in arr.tolist():
             assert fmt(io_lib, v) == "%.12E" % v, repr(v)
+
+
+# ---- parsers (initialise's file formats, d2q9-bgk.c:2736-2762 and :2844-2857) -----------
+def _bits_to_mask(ptr, nx, ny):
+    wpr = (nx + 31) // 32
+    words = np.ctypeslib.as_array(ptr, shape=(ny * wpr,)).reshape(ny, wpr)
+    return np.unpackbits(words.view(np.uint8).reshape(ny, wpr * 4), axis=1, bitorder="little")[:, :nx]
+
+
+@pytest.mark.parametrize("text,cells", [
+    ("", []),                                                  # no obstacles at all
+    ("0 0 1\n3 2 1\n", [(0, 0), (3, 2)]),
+    ("0 0 1\n0 0 1\n39 4 1", [(0, 0), (39, 4)]),               # duplicates, no trailing newline
+    ("  5 1 1 \r\n\n\n7   3\t1\r\n", [(5, 1), (7, 3)]),         # CRLF, blank lines, tabs
+    ("1 1 1 2 2 1 3 3 1", [(1, 1), (2, 2), (3, 3)]),           # fscanf treats any whitespace alike
+    ("33 0 1\n32 0 1\n31 0 1\n", [(33, 0), (32, 0), (31, 0)]),  # across a 32-bit word boundary
+])
+def test_obstacle_parser_accepts_what_fscanf_accepts(io_lib, tmp_path, text, cells):
+    nx, ny = 40, 5
+    f = tmp_path / "o.dat"
+    f.write_text(text)
+    io_lib.lbm_read_obstacle_bits.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    io_lib.lbm_read_obstacle_bits.restype = C.POINTER(C.c_uint32)
+    m = _bits_to_mask(io_lib.lbm_read_obstacle_bits(str(f).encode(), nx, ny), nx, ny)
+    want = np.zeros((ny, nx), dtype=np.uint8)
+    for x, y in cells:
+        want[y, x] = 1
+    assert np.array_equal(m, want)
+
+
+def test_param_parser_reads_float_and_double_views(io_lib, tmp_path):
+    import lbm_b200 as L
+    f = tmp_path / "p.params"
+    f.write_text("128\n256\n40000\n10\n0.1\n0.005\n1.85\n")
+    pf, pd = L.Param(), L.ParamF64()
+    io_lib.lbm_read_params.argtypes = [C.c_char_p, C.POINTER(L.Param), C.POINTER(L.ParamF64)]
+    io_lib.lbm_read_params.restype = None
+    io_lib.lbm_read_params(str(f).encode(), C.byref(pf), C.byref(pd))
+    assert (pf.nx, pf.ny, pf.maxIters, pf.reynolds_dim) == (128, 256, 40000, 10)
+    assert (pd.nx, pd.ny, pd.maxIters, pd.reynolds_dim) == (128, 256, 40000, 10)
+    assert np.float32(pf.density) == np.float32(0.1) and pd.density == 0.1      # %f vs %lf
+    assert np.float32(pf.accel) == np.float32(0.005) and pd.accel == 0.005
+    assert np.float32(pf.omega) == np.float32(1.85) and pd.omega == 1.85
