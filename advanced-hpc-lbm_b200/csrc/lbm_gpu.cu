@@ -242,16 +242,14 @@ class Grid : public GridBase {
     if (flags & LBM_GPU_KERNEL_SCALAR) kernel = LBM_GPU_KERNEL_SCALAR;
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
-    else kernel = (nx % 4 == 0) ? LBM_GPU_KERNEL_VEC4 : LBM_GPU_KERNEL_SCALAR;   // refined in choose_kernel()
-    if (kernel == LBM_GPU_KERNEL_VEC4 && nx % 4 != 0)
-      throw CudaError{"the vector kernel needs nx % 4 == 0"};
+    else kernel = LBM_GPU_KERNEL_VEC4;                         // refined in choose_kernel()
     if (flags & LBM_GPU_KERNEL_TMA) throw CudaError{"LBM_GPU_KERNEL_TMA is reserved: no TMA kernel in this build"};
   }
 
   // launch shape shared by the step kernels: blockDim (bx, by), tiles of bx*vec x by cells
   void tile_shape(int& vec, int& bx, int& by) const {
     vec = (kernel == LBM_GPU_KERNEL_SCALAR || (kernel == LBM_GPU_KERNEL_PERSISTENT && persistent_vec == 1)) ? 1 : 4;
-    const int nxv = prm.nx / vec;
+    const int nxv = (prm.nx + vec - 1) / vec;
     bx = (int)std::min<long long>(LBM_BLOCK_THREADS, round_up(nxv, 32));
     by = LBM_BLOCK_THREADS / bx;
   }
@@ -286,7 +284,7 @@ class Grid : public GridBase {
       persistent_vec = pv;
       int vec, bx, by;
       tile_shape(vec, bx, by);
-      return (long long)((prm.nx / vec + bx - 1) / bx) * ((slabs[0].rows + by - 1) / by);
+      return (long long)(((prm.nx + vec - 1) / vec + bx - 1) / bx) * ((slabs[0].rows + by - 1) / by);
     };
     // tiny grids: one cell per thread (4x the threads on the step's dependent-latency chain)
     // as long as that does not put more than kPersistScalarBlocks blocks on the grid barrier
@@ -294,7 +292,7 @@ class Grid : public GridBase {
     int cap = persistent_capacity(slabs[0]);
     long long scalar_limit = std::min<long long>(cap, kPersistScalarBlocks);
     if (const char* e = getenv("LBM_PERSIST_VEC")) scalar_limit = (atoi(e) == 1) ? cap : 0;   // experiments
-    if (tiles > scalar_limit && prm.nx % 4 == 0) {
+    if (tiles > scalar_limit) {
       tiles = tiles_for(4);
       cap = persistent_capacity(slabs[0]);
     }
@@ -459,7 +457,7 @@ class Grid : public GridBase {
 
     int vec, bx, by;
     tile_shape(vec, bx, by);
-    const int nxv = prm.nx / vec;
+    const int nxv = (prm.nx + vec - 1) / vec;
     const dim3 block(bx, by);
     if (kernel == LBM_GPU_KERNEL_PERSISTENT) {
       Slab<real>& s = slabs[0];

@@ -382,7 +382,7 @@ __device__ __forceinline__ void boundary_signal(const StepArgs<real>& a, const b
 
 // ------------------------------------------------------------------------------------
 // K1a  lbm_step_vec4: four cells per thread, 128-bit loads/stores straight from/to the
-// SoA planes (nx % 4 == 0).  x-shifted planes come from the aligned vector plus one
+// SoA planes (any nx: rows are padded to the pitch, a multiple of 32 elements).  x-shifted planes come from the aligned vector plus one
 // element of the neighbouring lane (warp shuffle); the two edge lanes of a warp fetch
 // that element with a scalar load that also implements the periodic wrap in x.
 // blockDim = (BX, BY), BX a multiple of 32 so that a warp never spans two rows.
@@ -452,9 +452,20 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
   in[0][7] = v7.y; in[1][7] = v7.z; in[2][7] = v7.w; in[3][7] = r7;
   in[0][8] = l8;   in[1][8] = v8.x; in[2][8] = v8.y; in[3][8] = v8.z;
 
+  // Widths that are not a multiple of 4: the row's last thread holds 1-3 valid cells, the
+  // rest of its vector is row padding (loaded and stored, never used).  The east neighbour
+  // of the last valid cell is column 0 -- the wrap element r3/r6/r7 already holds -- and the
+  // padding cells are treated as obstacles so that they add nothing to the average.
+  uint32_t obits = mbits;
+  const int nvalid = a.nx - xc;
+  if (nvalid < 4) {
+    in[nvalid - 1][3] = r3; in[nvalid - 1][6] = r6; in[nvalid - 1][7] = r7;
+    obits |= (0xFu << nvalid) & 0xFu;
+  }
+
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const real s = cell_update<real, STRICT>(in[j], (mbits >> j) & 1u, a.omega, out[j]);
+    const real s = cell_update<real, STRICT>(in[j], (obits >> j) & 1u, a.omega, out[j]);
     q += to_fixed(s);
     if (active && !(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);   // NaN / blow-up
   }

@@ -63,10 +63,10 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
                                       word [jj * ((nx + 31) / 32) + ii / 32]; for grids whose
                                       int mask does not fit in host memory */
 #define LBM_GPU_KERNEL_SCALAR  4u  /* force the one-cell-per-thread kernel (any nx) */
-#define LBM_GPU_KERNEL_TMA     8u  /* force the TMA-staged kernel (needs nx % 4 == 0) */
-#define LBM_GPU_KERNEL_VEC4   16u  /* force the 128-bit direct-load kernel (nx % 4 == 0) */
+#define LBM_GPU_KERNEL_TMA     8u  /* reserved: no TMA-staged kernel in this build (create fails) */
+#define LBM_GPU_KERNEL_VEC4   16u  /* force the 128-bit direct-load kernel (one launch per timestep) */
 #define LBM_GPU_KERNEL_PERSISTENT 64u /* force the persistent cooperative kernel (all steps of a run
-                                      in one launch; single GPU, nx % 4 == 0).  Chosen by default
+                                      in one launch; single GPU).  Chosen by default
                                       for grids small enough to live in L2 */
 #define LBM_GPU_POOL         128u  /* take the lattice from the device's stream-ordered memory pool and
                                       leave it there on destroy: a host that creates many lattices in

@@ -24,11 +24,11 @@ SHAPES = [
     (128, 128), (128, 256), (256, 64), (64, 7), (4, 2), (8, 3), (36, 5), (132, 9),
     (1024, 17), (2048, 6),
 ]
-ODD_SHAPES = [(1, 2), (3, 5), (37, 11), (129, 4), (250, 9), (33, 2)]
+ODD_SHAPES = [(1, 2), (2, 3), (3, 5), (5, 4), (37, 11), (129, 4), (250, 9), (33, 2), (127, 3), (130, 5), (515, 4)]
 
 
 def _kernels_for(nx):
-    return [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT] + ([L.KERNEL_VEC4] if nx % 4 == 0 else [])
+    return [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4]
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES + ODD_SHAPES)
@@ -103,7 +103,7 @@ def test_kernel_selection():
     with L.Lattice(130, 16, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_PERSISTENT          # one cell per thread
     with L.Lattice(4098, 4096, DENSITY, ACCEL, OMEGA) as lat:
-        assert lat.info().kernel == L.KERNEL_SCALAR
+        assert lat.info().kernel == L.KERNEL_VEC4                # any width
     with L.Lattice(4096, 4096, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_VEC4
     nx, ny = 1024, 600          # more tiles than resident blocks: every block loops
@@ -216,8 +216,8 @@ def test_degenerate_masks():
 def test_errors_are_reported_not_fatal():
     with pytest.raises(L.LbmError, match="ny >= 2"):
         L.Lattice(8, 1, DENSITY, ACCEL, OMEGA)
-    with pytest.raises(L.LbmError, match="nx % 4"):
-        L.Lattice(10, 4, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_VEC4)
+    with pytest.raises(L.LbmError, match="reserved"):
+        L.Lattice(16, 4, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_TMA)
     with L.Lattice(8, 4, DENSITY, ACCEL, OMEGA) as lat:
         with pytest.raises(L.LbmError, match="double precision|single precision"):
             L.load_library().lbm_gpu_run_f64(lat.h, 1, None) and L.binding._check(1)
