@@ -65,10 +65,11 @@ def test_make_check_passes_fp32(name, tmp_path, golden_dir):
     print(name, "av_vels %.3g%% pressure %.3g%%" % tuple(pcts))
 
 
-@pytest.mark.parametrize("name", ["128x128", "128x256"])
+@pytest.mark.parametrize("name", NAMES)
 def test_f64_kernel_reproduces_golden_files(name, tmp_path, golden_dir):
     """The double-precision build of the kernel is the golden generator's arithmetic: the
-    output files agree with check/*.dat to ~1e-10 relative over 40000 steps."""
+    output files agree with check/*.dat to ~1e-10 relative over the whole run (for 256x256
+    and 1024x1024 the final_state golden is the regenerated one, tests/golden/make_golden.py)."""
     run_cli(name, str(tmp_path), {"LBM_PRECISION": "f64"})
     rc, text, pcts = run_check(name, str(tmp_path), golden_dir)
     assert rc == 0, text
@@ -76,7 +77,8 @@ def test_f64_kernel_reproduces_golden_files(name, tmp_path, golden_dir):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     fs = np.loadtxt(os.path.join(str(tmp_path), "final_state.dat"))
     assert np.array_equal(fs[:, 6].reshape(g["obstacle"].shape), g["obstacle"])
-    assert np.max(np.abs(fs[:, 4].reshape(g["u"].shape) - g["u"])) < 1e-11
+    if "u" in g.files:
+        assert np.max(np.abs(fs[:, 4].reshape(g["u"].shape) - g["u"])) < 1e-11
 
 
 def test_multi_slab_cli_gives_identical_files(tmp_path):

@@ -32,9 +32,11 @@ def test_f64_oracle_reproduces_golden_av_vels_prefix(name, steps):
     assert rel.max() <= PRINT_EPS
 
 
-def test_f64_oracle_reproduces_golden_128x128_full_run():
-    """Whole 40000-step run: every av_vels value and all four final_state fields."""
-    name = "128x128"
+@pytest.mark.parametrize("name", ["128x128", "128x256"])
+def test_f64_oracle_reproduces_golden_full_run(name):
+    """Whole 40000-step runs of the two inputs whose golden final_state the reference ships:
+    every av_vels value and all four final_state fields (128x256 exercises the y-wrap:
+    rows 0 and 255 are open)."""
     nx, ny, iters, rho, acc, om, obst, cells = _setup(name, np.float64)
     g = np.load(os.path.join(GOLD, name + ".npz"))
     fin, av, _ = O.run(cells, obst, iters, rho, acc, om)
