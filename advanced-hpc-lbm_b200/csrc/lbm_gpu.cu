@@ -67,6 +67,7 @@ struct IpcDesc {
   unsigned long long off_sync;        // byte offset of the sync words inside the window
   unsigned long long steps_done;
   cudaIpcMemHandle_t handle;          // of the halo window (the lattice itself is never shared)
+  char gpu_uuid[16];                  // physical GPU: two flag-ordered slabs must not share one
 };
 static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large");
 constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
@@ -859,6 +860,9 @@ int lbm_gpu_ipc_export(lbm_gpu* h, void* desc) {
     d.off_sync = s.off_sync;
     d.steps_done = (unsigned long long)g.steps_done;
     CK(cudaIpcGetMemHandle(&d.handle, s.win));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s.device));
+    memcpy(d.gpu_uuid, prop.uuid.bytes, 16);
     memset(desc, 0, LBM_GPU_IPC_DESC_BYTES);
     memcpy(desc, &d, sizeof d);
   });
@@ -879,6 +883,13 @@ int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_abo
       if (d->nx != g.prm.nx || d->pitch != g.pitch) throw CudaError{"neighbour descriptor is for another grid width"};
       if (d->steps_done != (unsigned long long)g.steps_done) throw CudaError{"neighbour is at a different timestep"};
     }
+    cudaDeviceProp my_prop;
+    CK(cudaGetDeviceProperties(&my_prop, s.device));
+    for (const IpcDesc* d : {&dn, &up})
+      if (memcmp(d->gpu_uuid, my_prop.uuid.bytes, 16) == 0 &&
+          !(d->pid == (int32_t)getpid() && d->win_addr == (unsigned long long)(uintptr_t)s.win))
+        throw CudaError{"a neighbouring slab runs on the same physical GPU: kernels that wait on one another "
+                        "must not share a device (use lbm_gpu_create with n_gpus slabs in one process instead)"};
     if ((dn.row0 + dn.rows) % ny != s.row0 % ny) throw CudaError{"descriptor 'below' does not hold row0-1"};
     if ((s.row0 + s.rows) % ny != up.row0 % ny) throw CudaError{"descriptor 'above' does not hold row0+nrows"};
     auto map = [&](const IpcDesc& d, int slot) -> char* {

@@ -67,6 +67,19 @@ def test_flag_protocol_refuses_a_shared_device():
         L.Lattice(64, 8, D, A, W, n_gpus=2, device_ids=[0, 0], flags=L.SYNC_FLAGS)
 
 
+def test_slab_handles_refuse_a_shared_device():
+    """Two one-slab handles (the one-process-per-GPU form) on the SAME GPU would spin on each
+    other's flags inside kernels that may never be co-scheduled: connect refuses."""
+    nx, ny = 64, 8
+    a = L.Lattice(nx, ny, D, A, W, slab=(0, 4), device_ids=[0])
+    b = L.Lattice(nx, ny, D, A, W, slab=(4, 4), device_ids=[0])
+    try:
+        with pytest.raises(L.LbmError, match="same physical GPU|must not share"):
+            a.ipc_connect(b.ipc_export(), b.ipc_export())
+    finally:
+        a.close(); b.close()
+
+
 @pytest.mark.parametrize("mode", ["events", "flags"])
 def test_real_multi_gpu_equals_single(mode):
     n = min(ndev(), 4)
