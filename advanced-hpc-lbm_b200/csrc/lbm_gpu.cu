@@ -6,7 +6,6 @@
 #include "lbm_gpu.h"
 #include "lbm_kernels.cuh"
 
-#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -139,31 +138,21 @@ class Grid : public GridBase {
   bool is_f64() const override { return sizeof(real) == 8; }
 
   ~Grid() override {
-    const bool dbg = getenv("LBM_GPU_DEBUG_TIMING") != nullptr;
-    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
     for (auto& s : slabs) {
-      double t0 = now();
       cudaSetDevice(s.device);
       if (s.stream) cudaStreamSynchronize(s.stream);
-      double t1 = now();
       for (int i = 0; i < 2; i++)
         if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
-      double t2 = now();
       pool_free(s.staging, s);
       pool_free(s.base, s);
       if (s.stream) cudaStreamSynchronize(s.stream);
-      double t3 = now();
       if (s.av_lo) cudaFree(s.av_lo);
       if (s.win) cudaFree(s.win);
-      double t4 = now();
       if (s.ev0) cudaEventDestroy(s.ev0);
       if (s.ev1) cudaEventDestroy(s.ev1);
       for (int i = 0; i < 2; i++)
         if (s.step_ev[i]) cudaEventDestroy(s.step_ev[i]);
       if (s.stream) cudaStreamDestroy(s.stream);
-      double t5 = now();
-      if (dbg) fprintf(stderr, "[lbm destroy] sync %.2f ipc-close %.2f pool-free %.2f cudaFree(small) %.2f events/stream %.2f ms\n",
-                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
     }
   }
 
@@ -292,7 +281,8 @@ class Grid : public GridBase {
     long long tiles = tiles_for(1);
     int cap = persistent_capacity(slabs[0]);
     long long scalar_limit = std::min<long long>(cap, kPersistScalarBlocks);
-    if (const char* e = getenv("LBM_PERSIST_VEC")) scalar_limit = (atoi(e) == 1) ? cap : 0;   // experiments
+    if (const char* e = getenv("LBM_PERSIST_VEC"))      // measurement knob of profiles/r01_small_grids.md
+      scalar_limit = (atoi(e) == 1) ? cap : 0;
     if (tiles > scalar_limit) {
       tiles = tiles_for(4);
       cap = persistent_capacity(slabs[0]);
