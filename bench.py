@@ -42,11 +42,13 @@ sys.path.insert(0, ROOT)
 
 from tools.make_inputs import channel_mask  # noqa: E402
 
-NX = 16384
-ROWS_PER_GPU = 16384
+# LBM_BENCH_NX / LBM_BENCH_ROWS shrink the grid for the harness's own tests; the benchmark
+# contract is the default 16384 x 16384 per GPU.
+NX = int(os.environ.get("LBM_BENCH_NX", "16384"))
+ROWS_PER_GPU = int(os.environ.get("LBM_BENCH_ROWS", "16384"))
 DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
 BYTES_PER_UPDATE = 72.0            # 9 fp32 loads + 9 fp32 stores
-CPU_SAMPLE_ROWS = 1024             # CPU legs run a 16384 x 1024 slab of the same generator
+CPU_SAMPLE_ROWS = min(1024, ROWS_PER_GPU)   # CPU legs run a 16384 x 1024 slab of the same generator
 HBM_FALLBACK_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -225,7 +227,8 @@ def workload_config(args, world):
                         "%d rows per GPU" % (NX, ny, ny // world),
             "nx": NX, "ny": ny, "timesteps_per_step": args.timesteps,
             "density": DENSITY, "accel": ACCEL, "omega": OMEGA,
-            "l2": "inputs larger than L2 (19.3 GB lattice per GPU vs 126 MB), no flush needed",
+            "l2": "inputs larger than L2 (%.1f GB lattice per GPU vs 126 MB), no flush needed"
+                  % (NX * (ny // world) * 72 / 1e9),
             "parallelism": "row slabs, %d GPU(s), halo rows pushed by the step kernel over NVLink" % world}
 
 
