@@ -110,6 +110,8 @@ struct Slab {
   unsigned long long* dn_flag = nullptr;      // neighbour below's kFlagFromAbove
   void* ipc_mapped[2] = {nullptr, nullptr};   // pointers to close on destroy
   bool pooled = false;                        // base/staging came from the stream-ordered pool
+  alignas(64) CUtensorMap tmap[2];            // K1c: (x, row, plane) view of lattice[0], lattice[1], row boxes
+  alignas(64) CUtensorMap tmap_halo[2];       // same view, 4-element boxes (the x halo of a tile)
 };
 
 template <typename real> struct ParamT;
@@ -221,6 +223,35 @@ class Grid : public GridBase {
     s.staging = st;
   }
 
+  // K1c: one 3-D tensor map (x, row, plane) per lattice buffer, box = one row of a tile
+  void make_tensor_maps(Slab<real>& s) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) throw CudaError{"cuTensorMapEncodeTiled is not available in this driver"};
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)s.rows, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(real), (cuuint64_t)plane_stride(s) * sizeof(real)};
+    const cuuint32_t box[3] = {LBM_TMA_BOX, 1, 1};
+    const cuuint32_t hbox[3] = {4, 1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int b = 0; b < 2; b++) {
+      for (int h = 0; h < 2; h++) {
+        const CUresult r = ((EncodeFn)fn)(h ? &s.tmap_halo[b] : &s.tmap[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.lattice[b],
+                                          dims, strides, h ? hbox : box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+          char msg[96];
+          snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+          throw CudaError{msg};
+        }
+      }
+    }
+  }
+
   // window section: parity b, direction d (0 = "from below": speeds 2,5,6; 1 = "from above": 4,7,8)
   real* win_section(char* win, int b, int d) const { return (real*)win + (size_t)((b * 2 + d) * 3) * pitch; }
 
@@ -233,7 +264,10 @@ class Grid : public GridBase {
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
     else kernel = LBM_GPU_KERNEL_VEC4;                         // refined in choose_kernel()
-    if (flags & LBM_GPU_KERNEL_TMA) throw CudaError{"LBM_GPU_KERNEL_TMA is reserved: no TMA kernel in this build"};
+    if (flags & LBM_GPU_KERNEL_TMA) {
+      if (sizeof(real) != 4) throw CudaError{"the TMA kernel is built for single precision only"};
+      kernel = LBM_GPU_KERNEL_TMA;
+    }
   }
 
   // launch shape shared by the step kernels: blockDim (bx, by), tiles of bx*vec x by cells
@@ -241,6 +275,7 @@ class Grid : public GridBase {
     vec = (kernel == LBM_GPU_KERNEL_SCALAR || (kernel == LBM_GPU_KERNEL_PERSISTENT && persistent_vec == 1)) ? 1 : 4;
     const int nxv = (prm.nx + vec - 1) / vec;
     bx = (int)std::min<long long>(LBM_BLOCK_THREADS, round_up(nxv, 32));
+    if (kernel == LBM_GPU_KERNEL_TMA) bx = LBM_BLOCK_THREADS;     // one row of LBM_TMA_TILE cells per block
     by = LBM_BLOCK_THREADS / bx;
   }
 
@@ -263,7 +298,8 @@ class Grid : public GridBase {
   // After the slabs exist: grids small enough to be launch-latency bound (they live in
   // L2) run all their steps in one persistent cooperative kernel.
   void choose_kernel() {
-    const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT);
+    const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT |
+                                 LBM_GPU_KERNEL_TMA);
     const bool want = (kernel == LBM_GPU_KERNEL_PERSISTENT);
     if (!want && (forced || slabs.size() != 1 || slab_mode)) return;
     if (slabs.size() != 1 || slab_mode) throw CudaError{"the persistent kernel handles a single slab only"};
@@ -422,11 +458,18 @@ class Grid : public GridBase {
 
   // -------------------------------------------------------------------- run ----
   template <bool STRICT, bool MULTI>
-  void launch_step(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block) {
+  void launch_step(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block, int src) {
     if (kernel == LBM_GPU_KERNEL_SCALAR)
       lbm::lbm_step_scalar<real, STRICT, MULTI><<<grid, block, 0, s.stream>>>(a);
+    else if (kernel == LBM_GPU_KERNEL_TMA)
+      launch_tma<STRICT, MULTI>(s, a, grid, block, src);
     else
       lbm::lbm_step_vec4<real, STRICT, MULTI><<<grid, block, 0, s.stream>>>(a);
+  }
+  template <bool STRICT, bool MULTI>
+  void launch_tma(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block, int src) {
+    if constexpr (sizeof(real) == 4)
+      lbm::lbm_step_tma<STRICT, MULTI><<<grid, block, 0, s.stream>>>(a, s.tmap[src], s.tmap_halo[src]);
   }
 
   void run(int n_steps, double* sums_out) {
@@ -522,8 +565,8 @@ class Grid : public GridBase {
         a.aw1 = prm.density * prm.accel / (real)9;
         a.aw2 = prm.density * prm.accel / (real)36;
         const dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y));
-        if (strict) { if (use_flags) launch_step<true, true>(s, a, grid, block); else launch_step<true, false>(s, a, grid, block); }
-        else        { if (use_flags) launch_step<false, true>(s, a, grid, block); else launch_step<false, false>(s, a, grid, block); }
+        if (strict) { if (use_flags) launch_step<true, true>(s, a, grid, block, src); else launch_step<true, false>(s, a, grid, block, src); }
+        else        { if (use_flags) launch_step<false, true>(s, a, grid, block, src); else launch_step<false, false>(s, a, grid, block, src); }
         CK(cudaGetLastError());
         launches++;
         if (multi && !use_flags) CK(cudaEventRecord(s.step_ev[t & 1], s.stream));
@@ -720,6 +763,7 @@ int create_impl(const typename ParamT<real>::type* params, const real* cells_aos
       const long long ar = (long long)params->ny - 2;
       s.accel_row = (ar >= s.row0 && ar < s.row0 + s.rows) ? (int)(ar - s.row0) : LBM_NO_ROW;
       g->alloc_slab(s);
+      if (g->kernel == LBM_GPU_KERNEL_TMA) g->make_tensor_maps(s);
       g->load_slab(s, cells_aos ? cells_aos + (size_t)s.row0 * cell_row : nullptr,
                    obstacles ? (const char*)obstacles + (size_t)s.row0 * obst_row_bytes : nullptr, 0);
     }
@@ -821,6 +865,7 @@ int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows
     const long long ar = (long long)params->ny - 2;
     s.accel_row = (ar >= row0 && ar < row0 + nrows) ? (int)(ar - row0) : LBM_NO_ROW;
     g->alloc_slab(s);
+    if (g->kernel == LBM_GPU_KERNEL_TMA) g->make_tensor_maps(s);
     g->load_slab(s, cells_aos_rows, obstacles_rows, 0);
     if (g->kernel == LBM_GPU_KERNEL_PERSISTENT) throw CudaError{"the persistent kernel handles a single slab only"};
     if (nrows == params->ny) { g->connect_local(); g->prepare(); }   // whole grid in one slab

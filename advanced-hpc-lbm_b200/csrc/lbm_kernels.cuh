@@ -20,6 +20,7 @@
 //            the same arithmetic as accelerating in place before streaming
 //            (d2q9-bgk.c:229-260) without a separate kernel or a pre-pass.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -459,7 +460,9 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
   uint32_t obits = mbits;
   const int nvalid = a.nx - xc;
   if (nvalid < 4) {
-    in[nvalid - 1][3] = r3; in[nvalid - 1][6] = r6; in[nvalid - 1][7] = r7;
+    if (nvalid == 1) { in[0][3] = r3; in[0][6] = r6; in[0][7] = r7; }
+    else if (nvalid == 2) { in[1][3] = r3; in[1][6] = r6; in[1][7] = r7; }
+    else { in[2][3] = r3; in[2][6] = r6; in[2][7] = r7; }
     obits |= (0xFu << nvalid) & 0xFu;
   }
 
@@ -524,6 +527,140 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   const unsigned long long q = vec4_tile<real, STRICT, false>(a, tx, ty);
   block_accumulate(q, a.av_lo, a.av_hi);
   boundary_signal<real, MULTI>(a, is_boundary);
+}
+
+// ------------------------------------------------------------------------------------
+// K1c  lbm_step_tma (fp32, opt-in with LBM_GPU_KERNEL_TMA): the same step with the nine
+// pulled rows of a 512-cell tile staged in shared memory by the Tensor Memory Accelerator
+// (one 3-D tensor map per lattice buffer: x, row, plane).  The copy engine does the y part
+// of the propagate shift (box row = r - e_y).  It cannot do the x part: the innermost box
+// coordinate must be a multiple of 16 bytes -- x = 1 raises an illegal-instruction fault
+// (tools/probe/tma_probe.cu) -- so the x-shifted planes get a 4-element halo box on the
+// side they pull from and the threads read that one extra element from shared memory,
+// where K1a uses a warp shuffle.  The two ends of a row (periodic wrap in x) and the few
+// rows that read the halo window or the accelerated side row keep the direct-load path
+// (vec4_tile), chosen per block.  Built to measure whether staging buys anything over
+// K1a: it does not (profiles/r01_kernel_variants.md), every byte is used once either way.
+// ------------------------------------------------------------------------------------
+#define LBM_TMA_TILE (LBM_BLOCK_THREADS * 4)
+#define LBM_TMA_BOX (LBM_TMA_TILE < 256 ? LBM_TMA_TILE : 256)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool STRICT, bool MULTI>
+__global__ void __launch_bounds__(LBM_BLOCK_THREADS, LBM_MIN_BLOCKS)
+lbm_step_tma(const __grid_constant__ StepArgs<float> a, const __grid_constant__ CUtensorMap src_map,
+             const __grid_constant__ CUtensorMap halo_map) {
+  __shared__ alignas(128) float tile[9][LBM_TMA_TILE];
+  __shared__ alignas(128) float halo[9][32];          // [k][0..3]: planes 1,5,8 cells xt-4..xt-1; 3,6,7 xt+T..xt+T+3
+                                                      // (rows 128 B apart: TMA destinations are 128-byte aligned)
+  __shared__ alignas(8) unsigned long long mbar;
+  int tx, ty;
+  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  boundary_wait<float, MULTI>(a, is_boundary);
+
+  const int r = ty;                                   // blockDim = (LBM_BLOCK_THREADS, 1): one row per tile
+  const bool special = (r == 0) || (r == a.rows - 1) || (r == a.accel_row) || (r - 1 == a.accel_row) ||
+                       (r + 1 == a.accel_row);
+  unsigned long long q = 0ULL;
+  if (special) {
+    q = vec4_tile<float, STRICT, false>(a, tx, ty);
+  } else {
+    const int tid = threadIdx.x;
+    const int xt = tx * LBM_TMA_TILE;                 // first column of the tile
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)),
+                   "r"((uint32_t)((9 * LBM_TMA_TILE + 6 * 4) * sizeof(float))) : "memory");
+      // e_k of d2q9-bgk.c:7-13: the value pulled into (x, r) for speed k sits at (x - ex, r - ey).
+      // A TMA box is at most 256 elements per dimension: LBM_TMA_TILE / 256 boxes per plane,
+      // plus a 4-element box left of the tile (ex = +1) or right of it (ex = -1).
+#define LBM_TMA_LOAD(k, ex, ey)                                                                                  \
+  _Pragma("unroll") for (int b = 0; b < LBM_TMA_TILE / LBM_TMA_BOX; b++)                                        \
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" \
+                 ::"r"(smem_u32(&tile[k][b * LBM_TMA_BOX])), "l"(&src_map), "r"(smem_u32(&mbar)),                 \
+                 "r"(xt + b * LBM_TMA_BOX), "r"(r - (ey)), "r"(k) : "memory");                                   \
+  if ((ex) != 0)                                                                                                 \
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" \
+                 ::"r"(smem_u32(&halo[k][0])), "l"(&halo_map), "r"(smem_u32(&mbar)),                              \
+                 "r"((ex) > 0 ? xt - 4 : xt + LBM_TMA_TILE), "r"(r - (ey)), "r"(k) : "memory")
+      LBM_TMA_LOAD(0, 0, 0);  LBM_TMA_LOAD(1, 1, 0);   LBM_TMA_LOAD(2, 0, 1);
+      LBM_TMA_LOAD(3, -1, 0); LBM_TMA_LOAD(4, 0, -1);  LBM_TMA_LOAD(5, 1, 1);
+      LBM_TMA_LOAD(6, -1, 1); LBM_TMA_LOAD(7, -1, -1); LBM_TMA_LOAD(8, 1, -1);
+#undef LBM_TMA_LOAD
+    }
+    const int x0 = xt + tid * 4;
+    const bool active = x0 < a.nx;
+    const int xc = active ? x0 : 0;
+    const long long PS = a.plane_stride;
+    const long long oC = (long long)r * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
+    // the wrap elements at the two ends of the row come by ordinary loads (the tensor map
+    // zero-fills x < 0 and reads row padding beyond nx)
+    const bool need_w = active && (x0 == 0);
+    const bool need_e = active && (x0 + 4 >= a.nx);
+    float w1e = 0, w5e = 0, w8e = 0, e3e = 0, e6e = 0, e7e = 0;
+    if (need_w) {
+      w1e = a.src[1 * PS + oC + a.nx - 1]; w5e = a.src[5 * PS + oS + a.nx - 1]; w8e = a.src[8 * PS + oN + a.nx - 1];
+    }
+    if (need_e) { e3e = a.src[3 * PS + oC]; e6e = a.src[6 * PS + oS]; e7e = a.src[7 * PS + oN]; }
+    const uint32_t mword = a.mask[(long long)r * a.mask_pitch + (xc >> 5)];
+    uint32_t obits = (mword >> (xc & 31)) & 0xFu;
+
+    {   // wait for the rows (phase 0 of a barrier used once)
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.b32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    }
+    float in[4][9], out[4][9];
+#define LBM_ROW(k) (*reinterpret_cast<const float4*>(&tile[k][tid * 4]))
+#define LBM_WEST(k) (tid == 0 ? halo[k][3] : tile[k][tid * 4 - 1])
+#define LBM_EAST(k) (tid == LBM_BLOCK_THREADS - 1 ? halo[k][0] : tile[k][tid * 4 + 4])
+    { const float4 v = LBM_ROW(0); in[0][0] = v.x; in[1][0] = v.y; in[2][0] = v.z; in[3][0] = v.w; }
+    { const float4 v = LBM_ROW(2); in[0][2] = v.x; in[1][2] = v.y; in[2][2] = v.z; in[3][2] = v.w; }
+    { const float4 v = LBM_ROW(4); in[0][4] = v.x; in[1][4] = v.y; in[2][4] = v.z; in[3][4] = v.w; }
+    { const float4 v = LBM_ROW(1); in[0][1] = LBM_WEST(1); in[1][1] = v.x; in[2][1] = v.y; in[3][1] = v.z; }
+    { const float4 v = LBM_ROW(5); in[0][5] = LBM_WEST(5); in[1][5] = v.x; in[2][5] = v.y; in[3][5] = v.z; }
+    { const float4 v = LBM_ROW(8); in[0][8] = LBM_WEST(8); in[1][8] = v.x; in[2][8] = v.y; in[3][8] = v.z; }
+    { const float4 v = LBM_ROW(3); in[0][3] = v.y; in[1][3] = v.z; in[2][3] = v.w; in[3][3] = LBM_EAST(3); }
+    { const float4 v = LBM_ROW(6); in[0][6] = v.y; in[1][6] = v.z; in[2][6] = v.w; in[3][6] = LBM_EAST(6); }
+    { const float4 v = LBM_ROW(7); in[0][7] = v.y; in[1][7] = v.z; in[2][7] = v.w; in[3][7] = LBM_EAST(7); }
+#undef LBM_ROW
+#undef LBM_WEST
+#undef LBM_EAST
+    if (need_w) { in[0][1] = w1e; in[0][5] = w5e; in[0][8] = w8e; }
+    if (need_e) {
+      const int nvalid = a.nx - x0;
+      if (nvalid == 1) { in[0][3] = e3e; in[0][6] = e6e; in[0][7] = e7e; }
+      else if (nvalid == 2) { in[1][3] = e3e; in[1][6] = e6e; in[1][7] = e7e; }
+      else if (nvalid == 3) { in[2][3] = e3e; in[2][6] = e6e; in[2][7] = e7e; }
+      else { in[3][3] = e3e; in[3][6] = e6e; in[3][7] = e7e; }
+      if (nvalid < 4) obits |= (0xFu << nvalid) & 0xFu;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float s = cell_update<float, STRICT>(in[j], (obits >> j) & 1u, a.omega, out[j]);
+      q += to_fixed(s);
+      if (active && !(s < (float)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);
+    }
+    if (active) {
+      float* d = a.dst + oC + x0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        Vec4<float> v; v.x = out[0][k]; v.y = out[1][k]; v.z = out[2][k]; v.w = out[3][k];
+        st4(d + k * PS, v);
+      }
+    } else {
+      q = 0ULL;
+    }
+  }
+  block_accumulate(q, a.av_lo, a.av_hi);
+  boundary_signal<float, MULTI>(a, is_boundary);
 }
 
 // ------------------------------------------------------------------------------------

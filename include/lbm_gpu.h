@@ -63,7 +63,8 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
                                       word [jj * ((nx + 31) / 32) + ii / 32]; for grids whose
                                       int mask does not fit in host memory */
 #define LBM_GPU_KERNEL_SCALAR  4u  /* force the one-cell-per-thread kernel (any nx) */
-#define LBM_GPU_KERNEL_TMA     8u  /* reserved: no TMA-staged kernel in this build (create fails) */
+#define LBM_GPU_KERNEL_TMA     8u  /* force the TMA-staged kernel (fp32; measured equal/slower than
+                                      VEC4, kept as the comparison point) */
 #define LBM_GPU_KERNEL_VEC4   16u  /* force the 128-bit direct-load kernel (one launch per timestep) */
 #define LBM_GPU_KERNEL_PERSISTENT 64u /* force the persistent cooperative kernel (all steps of a run
                                       in one launch; single GPU).  Chosen by default

@@ -62,6 +62,16 @@ def test_slabs_strict_equal_oracle():
         assert np.array_equal(lat.download(), ref)
 
 
+def test_tma_kernel_slabs_equal_single_slab():
+    nx, ny, n, steps = 1100, 40, 3, 8
+    cells, obst = O.random_lattice(nx, ny, seed=17, p_obst=0.03)
+    ref, av_ref, _ = single(nx, ny, cells, obst, steps)
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, n_gpus=n, device_ids=[0] * n,
+                   flags=L.KERNEL_TMA) as lat:
+        av = lat.run(steps)
+        assert np.array_equal(lat.download(), ref) and np.array_equal(av, av_ref)
+
+
 def test_flag_protocol_refuses_a_shared_device():
     with pytest.raises(L.LbmError, match="own GPU"):
         L.Lattice(64, 8, D, A, W, n_gpus=2, device_ids=[0, 0], flags=L.SYNC_FLAGS)

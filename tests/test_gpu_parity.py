@@ -22,13 +22,13 @@ DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
 
 SHAPES = [
     (128, 128), (128, 256), (256, 64), (64, 7), (4, 2), (8, 3), (36, 5), (132, 9),
-    (1024, 17), (2048, 6),
+    (1024, 17), (2048, 6), (1540, 12),
 ]
 ODD_SHAPES = [(1, 2), (2, 3), (3, 5), (5, 4), (37, 11), (129, 4), (250, 9), (33, 2), (127, 3), (130, 5), (515, 4)]
 
 
 def _kernels_for(nx):
-    return [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4]
+    return [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4, L.KERNEL_TMA]
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES + ODD_SHAPES)
@@ -79,10 +79,10 @@ def test_rest_state_and_obstacle_bits():
     assert np.array_equal(b, ref)
 
 
-@pytest.mark.parametrize("kernel", ["vec4", "persistent", "scalar"])
+@pytest.mark.parametrize("kernel", ["vec4", "persistent", "scalar", "tma"])
 def test_chunked_runs_equal_one_run(kernel):
     """run(a); run(b) == run(a+b): no state is lost between calls (odd and even splits)."""
-    k = {"vec4": L.KERNEL_VEC4, "persistent": L.KERNEL_PERSISTENT, "scalar": L.KERNEL_SCALAR}[kernel]
+    k = {"vec4": L.KERNEL_VEC4, "persistent": L.KERNEL_PERSISTENT, "scalar": L.KERNEL_SCALAR, "tma": L.KERNEL_TMA}[kernel]
     nx, ny = 128, 24
     cells, obst = O.random_lattice(nx, ny, seed=11)
     with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
@@ -216,8 +216,8 @@ def test_degenerate_masks():
 def test_errors_are_reported_not_fatal():
     with pytest.raises(L.LbmError, match="ny >= 2"):
         L.Lattice(8, 1, DENSITY, ACCEL, OMEGA)
-    with pytest.raises(L.LbmError, match="reserved"):
-        L.Lattice(16, 4, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_TMA)
+    with pytest.raises(L.LbmError, match="single precision only"):
+        L.Lattice(16, 4, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_TMA, f64=True)
     with L.Lattice(8, 4, DENSITY, ACCEL, OMEGA) as lat:
         with pytest.raises(L.LbmError, match="double precision|single precision"):
             L.load_library().lbm_gpu_run_f64(lat.h, 1, None) and L.binding._check(1)

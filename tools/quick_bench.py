@@ -19,8 +19,11 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--kernel", default="auto")
 ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--f64", action="store_true")
+ap.add_argument("--sync-flags", action="store_true", help="in-process multi-GPU ordered by device flags")
 a = ap.parse_args()
 flags = {"auto": 0, "scalar": L.KERNEL_SCALAR, "vec4": L.KERNEL_VEC4, "tma": L.KERNEL_TMA, "persistent": L.KERNEL_PERSISTENT}[a.kernel]
+if a.sync_flags:
+    flags |= L.SYNC_FLAGS
 t0 = time.time()
 mask = channel_mask(a.nx, a.ny)
 bits = L.pack_obstacle_bits(mask)
