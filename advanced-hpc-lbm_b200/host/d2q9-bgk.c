@@ -16,6 +16,10 @@
  *   LBM_SKIP_FINAL_STATE=1 do not write final_state.dat (huge synthetic grids: 16384^2
  *                          would be 24 GB of text)
  *   LBM_REPORT=1           print MLUPS / GB/s / device time after the contract lines
+ *   LBM_DEBUG=1            the reference's -DDEBUG output (d2q9-bgk.c:196-200): after every
+ *                          timestep print its number, average velocity and total density
+ *                          (one lbm_gpu_run + lbm_gpu_digest per step: slow, for eyeballing
+ *                          mass conservation)
  */
 #define _POSIX_C_SOURCE 200809L
 #include <math.h>
@@ -97,7 +101,21 @@ int main(int argc, char* argv[])
   const double init_toc = wtime();
   const double comp_tic = init_toc;
 
-  if (f64) {
+  if (env_flag("LBM_DEBUG")) {
+    for (int tt = 0; tt < iters; tt++) {
+      double density;
+      if (f64) {
+        GPU(lbm_gpu_run_f64(gpu, 1, &av_vels[tt]));
+      } else {
+        GPU(lbm_gpu_run(gpu, 1, &av_vels_f[tt]));
+        av_vels[tt] = av_vels_f[tt];
+      }
+      GPU(lbm_gpu_digest(gpu, &density, NULL));
+      printf("==timestep: %d==\n", tt);
+      printf("av velocity: %.12E\n", av_vels[tt]);
+      printf("tot density: %.12E\n", density);
+    }
+  } else if (f64) {
     GPU(lbm_gpu_run_f64(gpu, iters, av_vels));
   } else {
     GPU(lbm_gpu_run(gpu, iters, av_vels_f));

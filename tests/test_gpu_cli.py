@@ -92,3 +92,25 @@ def test_multi_slab_cli_gives_identical_files(tmp_path):
     run_cli("128x256", str(b), {"LBM_GPUS": str(n)})
     for f in ("av_vels.dat", "final_state.dat"):
         assert open(os.path.join(str(a), f), "rb").read() == open(os.path.join(str(b), f), "rb").read()
+
+
+def test_debug_mode_prints_reference_debug_lines(tmp_path):
+    """LBM_DEBUG=1 reproduces the reference's -DDEBUG block (d2q9-bgk.c:196-200) and the total
+    density it prints stays constant (mass conservation)."""
+    p = tmp_path / "small.params"
+    p.write_text("64\n32\n25\n10\n0.1\n0.005\n1.85\n")
+    o = tmp_path / "small.dat"
+    o.write_text("".join("%d 0 1\n%d 31 1\n" % (x, x) for x in range(64)))
+    env = dict(os.environ, LBM_DEBUG="1")
+    r = subprocess.run([EXE, str(p), str(o)], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "==timestep: 0==" and lines[3] == "==timestep: 1=="
+    dens = [float(l.split(":")[1]) for l in lines if l.startswith("tot density:")]
+    avs = [float(l.split(":")[1]) for l in lines if l.startswith("av velocity:")]
+    assert len(dens) == 25 and len(avs) == 25
+    assert abs(dens[0] - 64 * 32 * 0.1) < 1e-3 and max(dens) - min(dens) < 1e-4
+    file_avs = np.loadtxt(os.path.join(str(tmp_path), "av_vels.dat"), usecols=[1])
+    np.testing.assert_allclose(avs, file_avs, rtol=1e-12)
+    assert "==done==" in lines
