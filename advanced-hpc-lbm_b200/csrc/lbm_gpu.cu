@@ -15,12 +15,17 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
 namespace {
 
 thread_local std::string g_error;
+
+struct CachedWindow { int device; size_t bytes; char* ptr; };
+std::mutex g_window_mutex;
+std::vector<CachedWindow> g_window_cache;     // windows of destroyed LBM_GPU_POOL lattices
 
 int fail(const char* fmt, ...) {
   char buf[1024];
@@ -145,11 +150,11 @@ class Grid : public GridBase {
       if (s.stream) cudaStreamSynchronize(s.stream);
       for (int i = 0; i < 2; i++)
         if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
+      pool_free(s.av_lo, s);
       pool_free(s.staging, s);
       pool_free(s.base, s);
       if (s.stream) cudaStreamSynchronize(s.stream);
-      if (s.av_lo) cudaFree(s.av_lo);
-      if (s.win) cudaFree(s.win);
+      window_free(s);
       if (s.ev0) cudaEventDestroy(s.ev0);
       if (s.ev1) cudaEventDestroy(s.ev1);
       for (int i = 0; i < 2; i++)
@@ -187,6 +192,32 @@ class Grid : public GridBase {
     if (s.pooled) cudaFreeAsync(p, s.stream);
     else cudaFree(p);
   }
+  // The halo window must be a plain cudaMalloc allocation (CUDA IPC), and a plain cudaFree
+  // is a device-wide synchronisation that was measured to take up to 0.6 s when it follows
+  // large transfers.  With LBM_GPU_POOL a destroyed lattice parks its window in a small
+  // per-process cache instead and the next lattice of the same width picks it up.
+  void window_alloc(Slab<real>& s) {
+    if (use_pool()) {
+      std::lock_guard<std::mutex> lock(g_window_mutex);
+      for (size_t i = 0; i < g_window_cache.size(); i++)
+        if (g_window_cache[i].device == s.device && g_window_cache[i].bytes == s.win_bytes) {
+          s.win = g_window_cache[i].ptr;
+          g_window_cache.erase(g_window_cache.begin() + i);
+          return;
+        }
+    }
+    CK(cudaMalloc((void**)&s.win, s.win_bytes));
+  }
+  void window_free(Slab<real>& s) {
+    if (!s.win) return;
+    if (use_pool()) {
+      std::lock_guard<std::mutex> lock(g_window_mutex);
+      g_window_cache.push_back({s.device, s.win_bytes, s.win});
+    } else {
+      cudaFree(s.win);
+    }
+    s.win = nullptr;
+  }
 
   // ---------------------------------------------------------------- allocation ----
   void alloc_slab(Slab<real>& s) {
@@ -211,7 +242,7 @@ class Grid : public GridBase {
     // driver block with anything else (it is exported over CUDA IPC)
     s.off_sync = round_up((size_t)12 * pitch * sizeof(real), 256);
     s.win_bytes = round_up(s.off_sync + kSyncWords * sizeof(unsigned long long), 2u << 20);
-    CK(cudaMalloc((void**)&s.win, s.win_bytes));
+    window_alloc(s);
     s.sync = (unsigned long long*)(s.win + s.off_sync);
     CK(cudaEventCreate(&s.ev0));
     CK(cudaEventCreate(&s.ev1));
@@ -479,10 +510,12 @@ class Grid : public GridBase {
     for (auto& s : slabs) {
       CK(cudaSetDevice(s.device));
       if (s.av_cap < (size_t)n_steps) {
-        if (s.av_lo) CK(cudaFree(s.av_lo));
+        pool_free(s.av_lo, s);
         s.av_lo = nullptr;
         s.av_cap = std::max<size_t>((size_t)n_steps, 1024);
-        CK(cudaMalloc((void**)&s.av_lo, 2 * s.av_cap * sizeof(unsigned long long)));
+        void* av = nullptr;
+        pool_alloc(&av, 2 * s.av_cap * sizeof(unsigned long long), s);
+        s.av_lo = (unsigned long long*)av;
         s.av_hi = s.av_lo + s.av_cap;
       }
       CK(cudaMemsetAsync(s.av_lo, 0, 2 * s.av_cap * sizeof(unsigned long long), s.stream));

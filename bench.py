@@ -352,11 +352,17 @@ def main():
         out = [L.PinnedArray((nrows, NX), np.float32) for _ in range(4)]
         av_host = np.empty(T, dtype=np.float32)
 
+        verbose = bool(os.environ.get("LBM_BENCH_VERBOSE"))
+
         def one_e2e_step():
-            lt = make_lattice()
-            lt.run(T, out=av_host)
-            lt.final_fields(out=[o.array for o in out])
-            lt.close()
+            t = [time.perf_counter()]
+            lt = make_lattice(); t.append(time.perf_counter())
+            lt.run(T, out=av_host); t.append(time.perf_counter())
+            lt.final_fields(out=[o.array for o in out]); t.append(time.perf_counter())
+            lt.close(); t.append(time.perf_counter())
+            if verbose and rank == 0:
+                sys.stderr.write("e2e step: create %.1f run %.1f fields %.1f destroy %.1f ms\n"
+                                 % tuple(1e3 * (b - a) for a, b in zip(t, t[1:])))
 
         one_e2e_step()                       # warm-up (first touch of the pinned pages etc.)
         barrier()

@@ -34,14 +34,15 @@ def bar():
         dist.barrier()
 
 
-for it in range(3):
+for it in range(5):
     bar()
     t = [time.perf_counter()]
     if world == 1:
-        lat = L.Lattice(NX, ny, 0.1, 0.005, 1.85, obstacles=pin.array)
+        lat = L.Lattice(NX, ny, 0.1, 0.005, 1.85, obstacles=pin.array, flags=L.POOL)
         t.append(time.perf_counter()); t.append(t[-1]); t.append(t[-1])
     else:
-        lat = L.Lattice(NX, ny, 0.1, 0.005, 1.85, obstacles=pin.array, slab=(row0, nrows), device_ids=[local])
+        lat = L.Lattice(NX, ny, 0.1, 0.005, 1.85, obstacles=pin.array, slab=(row0, nrows), device_ids=[local],
+                        flags=L.POOL)
         t.append(time.perf_counter())
         below, above = slabs.exchange_descriptors(lat.ipc_export(), rank, world, dist)
         lat.ipc_connect(below, above)
