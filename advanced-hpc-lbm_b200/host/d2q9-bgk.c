@@ -172,7 +172,7 @@ int main(int argc, char* argv[])
     if (fp == NULL) die("could not open file output file", __LINE__, __FILE__);
     static char big[1 << 22];
     setvbuf(fp, big, _IOFBF, sizeof big);
-    long long chunk = (8LL << 20) / nx;       /* rows per block: about 8 M cells */
+    long long chunk = (2LL << 20) / nx;       /* rows per block: about 2 M cells (~200 MB of text) */
     if (chunk < 1) chunk = 1;
     if (chunk > ny) chunk = ny;
     const size_t n = (size_t)chunk * (size_t)nx;

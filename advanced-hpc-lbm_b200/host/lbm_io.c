@@ -212,17 +212,13 @@ static char* put_int(char* o, long long v)
   return o;
 }
 
-void lbm_write_final_state_rows(void* fpv, int nx, long long row0, long long nrows,
-                                const double* u_x, const double* u_y, const double* u,
-                                const double* pressure, const uint32_t* obstacle_bits)
+/* formats rows [r_begin, r_end) of a block into buf; returns the number of bytes */
+static size_t format_rows(char* buf, int nx, long long row0, long long r_begin, long long r_end,
+                          const double* u_x, const double* u_y, const double* u, const double* pressure,
+                          const uint32_t* obstacle_bits)
 {
-  FILE* fp = (FILE*)fpv;
-  enum { LINE_MAX_BYTES = 160, CHUNK = 4096 };
-  char* buf = (char*)malloc((size_t)CHUNK * LINE_MAX_BYTES);
-  if (buf == NULL) die("cannot allocate memory for output rows", __LINE__, __FILE__);
   char* o = buf;
-  int lines = 0;
-  for (long long r = 0; r < nrows; r++) {
+  for (long long r = r_begin; r < r_end; r++) {
     const long long jj = row0 + r;
     for (int ii = 0; ii < nx; ii++) {
       const size_t n = (size_t)r * (size_t)nx + (size_t)ii;
@@ -239,15 +235,40 @@ void lbm_write_final_state_rows(void* fpv, int nx, long long row0, long long nro
       o += lbm_format_e12(o, pressure[n]); *o++ = ' ';
       *o++ = (char)('0' + lbm_obstacle_bit(obstacle_bits, nx, ii, (int)jj));
       *o++ = '\n';
-      if (++lines == CHUNK) {
-        if (fwrite(buf, 1, (size_t)(o - buf), fp) != (size_t)(o - buf)) die("could not write output file", __LINE__, __FILE__);
-        o = buf;
-        lines = 0;
-      }
     }
   }
-  if (o != buf && fwrite(buf, 1, (size_t)(o - buf), fp) != (size_t)(o - buf)) die("could not write output file", __LINE__, __FILE__);
-  free(buf);
+  return (size_t)(o - buf);
+}
+
+/* The block is cut into pieces that are formatted in parallel (OpenMP, if the host was
+ * built with it) and written in order: the text is identical for any thread count. */
+void lbm_write_final_state_rows(void* fpv, int nx, long long row0, long long nrows,
+                                const double* u_x, const double* u_y, const double* u,
+                                const double* pressure, const uint32_t* obstacle_bits)
+{
+  FILE* fp = (FILE*)fpv;
+  enum { LINE_MAX_BYTES = 128 };          /* 2 ints (<= 11 chars) + 4 x 19 chars + flag + separators */
+  if (!pow5_ready) pow5_init();           /* before the threads start */
+  long long pieces = nrows < 64 ? nrows : 64;
+  if (pieces < 1) return;
+  char** bufs = (char**)calloc((size_t)pieces, sizeof(char*));
+  size_t* lens = (size_t*)calloc((size_t)pieces, sizeof(size_t));
+  if (bufs == NULL || lens == NULL) die("cannot allocate memory for output rows", __LINE__, __FILE__);
+  int failed = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long long p = 0; p < pieces; p++) {
+    const long long rb = nrows * p / pieces, re = nrows * (p + 1) / pieces;
+    bufs[p] = (char*)malloc((size_t)(re - rb) * (size_t)nx * LINE_MAX_BYTES + 1);
+    if (bufs[p] == NULL) { failed = 1; continue; }
+    lens[p] = format_rows(bufs[p], nx, row0, rb, re, u_x, u_y, u, pressure, obstacle_bits);
+  }
+  if (failed) die("cannot allocate memory for output rows", __LINE__, __FILE__);
+  for (long long p = 0; p < pieces; p++) {
+    if (lens[p] && fwrite(bufs[p], 1, lens[p], fp) != lens[p]) die("could not write output file", __LINE__, __FILE__);
+    free(bufs[p]);
+  }
+  free(bufs);
+  free(lens);
 }
 
 void lbm_write_av_vels(const char* path, int n, const double* av_vels)

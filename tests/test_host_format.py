@@ -15,7 +15,7 @@ HOST = os.path.join(ROOT, "advanced-hpc-lbm_b200", "host")
 @pytest.fixture(scope="module")
 def io_lib(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("io") / "liblbm_io_test.so")
-    subprocess.check_call(["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-fopenmp", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
                            "-I" + HOST, os.path.join(HOST, "lbm_io.c"), "-lm", "-o", so])
     lib = C.CDLL(so)
     lib.lbm_format_e12.argtypes = [C.c_char_p, C.c_double]
@@ -95,3 +95,32 @@ def test_param_parser_reads_float_and_double_views(io_lib, tmp_path):
     assert np.float32(pf.density) == np.float32(0.1) and pd.density == 0.1      # %f vs %lf
     assert np.float32(pf.accel) == np.float32(0.005) and pd.accel == 0.005
     assert np.float32(pf.omega) == np.float32(1.85) and pd.omega == 1.85
+
+
+def test_final_state_writer_is_identical_to_fprintf(io_lib, tmp_path):
+    """The parallel block writer against Python's own %-formatting of the same values (the
+    reference's fprintf line, d2q9-bgk.c:2978), on a block with more rows than pieces."""
+    nx, nrows, row0 = 37, 150, 1000
+    rng = np.random.default_rng(5)
+    f = [(10.0 ** rng.uniform(-9, 0, nrows * nx) * rng.choice([-1.0, 1.0], nrows * nx)).astype(np.float32).astype(np.float64)
+         for _ in range(4)]
+    ny = row0 + nrows
+    mask = (rng.random((ny, nx)) < 0.2)
+    bits = np.zeros((ny, (nx + 31) // 32), dtype=np.uint32)
+    ys, xs = np.nonzero(mask)
+    np.bitwise_or.at(bits, (ys, xs // 32), (np.uint32(1) << (xs % 32).astype(np.uint32)))
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    path = str(tmp_path / "fs.dat")
+    fp = libc.fopen(path.encode(), b"w")
+    io_lib.lbm_write_final_state_rows.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong] + [C.c_void_p] * 5
+    io_lib.lbm_write_final_state_rows.restype = None
+    io_lib.lbm_write_final_state_rows(fp, nx, row0, nrows, *[a.ctypes.data_as(C.c_void_p) for a in f],
+                                      bits.ctypes.data_as(C.c_void_p))
+    libc.fclose(fp)
+    want = "".join("%d %d %.12E %.12E %.12E %.12E %d\n" % (i, row0 + r, f[0][r * nx + i], f[1][r * nx + i], f[2][r * nx + i],
+                                                        f[3][r * nx + i], int(mask[row0 + r, i]))
+                   for r in range(nrows) for i in range(nx))
+    assert open(path).read() == want
