@@ -192,6 +192,23 @@ def test_blown_up_lattice_reports_nan_like_the_reference():
     assert np.isnan(av_ref[0])
 
 
+@pytest.mark.parametrize("density,accel,omega", [(0.1, 1.2, 1.85), (0.3, 0.9, 1.0), (0.05, 2.5, 0.6), (1.0, 0.001, 1.99)])
+def test_other_parameters_and_the_accelerate_guard(density, accel, omega):
+    """Parameters far from the shipped ones; with a large accel the guard of accelerate_flow
+    (d2q9-bgk.c:247-249) is false for part of row ny-2.  Every kernel, one slab and three."""
+    nx, ny, steps = 132, 9, 4
+    cells, obst = O.random_lattice(nx, ny, seed=31, density=density)
+    ref, _, av_ref = O.run(cells, obst, steps, density, accel, omega)
+    for k in _kernels_for(nx):
+        for n in ((1, 3) if k != L.KERNEL_PERSISTENT else (1,)):
+            with L.Lattice(nx, ny, density, accel, omega, cells=cells, obstacles=obst, flags=L.STRICT | k,
+                           n_gpus=n, device_ids=[0] * n) as lat:
+                av = lat.run(steps)
+                assert np.array_equal(lat.download().view(np.uint32), ref.view(np.uint32)), (k, n)
+            ok = np.isfinite(av_ref)
+            np.testing.assert_allclose(av[ok].astype(np.float64), av_ref[ok], rtol=1e-6)
+
+
 def test_degenerate_masks():
     """No obstacle file at all (obstacles=NULL), and a grid that is all obstacles: the
     reference divides by tot_cells = 0 there (d2q9-bgk.c:1811) and gets NaN; so do we."""

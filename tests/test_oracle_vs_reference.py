@@ -104,3 +104,26 @@ def test_openmp_annotated_reference_matches_serial_lattice():
     rel = np.abs(a.astype(np.float64) - b) / np.abs(a)
     assert rel.max() < 2e-6
     assert abs(av_a - av_b) < 1e-6 * abs(av_a)
+
+
+@pytest.mark.parametrize("density,accel,omega", [(0.1, 1.2, 1.85), (0.3, 0.9, 1.0), (0.05, 2.5, 0.6), (1.0, 0.001, 1.99)])
+def test_other_parameters_and_the_accelerate_guard(density, accel, omega):
+    """Parameters far from the shipped ones.  With a large accel the guard of accelerate_flow
+    (f3 - w1 > 0 && f6 - w2 > 0 && f7 - w2 > 0, d2q9-bgk.c:247-249) is false for part of the
+    row, which the shipped inputs never exercise."""
+    lib = _lib("f32_strict")
+    nx, ny = 48, 9
+    cells, obst = O.random_lattice(nx, ny, seed=31, density=density)
+    w1 = np.float32(density) * np.float32(accel) / np.float32(9)
+    row = cells[ny - 2, :, 3]
+    if accel in (1.2, 0.9):
+        assert ((row - w1) > 0).any() and ((row - w1) <= 0).any()      # both branches taken
+    if accel == 2.5:
+        assert not ((row - w1) > 0).any()                               # guard false everywhere
+    for _ in range(3):
+        ra, rb, rav = O.ref_timestep_new2(lib, cells, obst, density, accel, omega)
+        oa, ob, oav = O.timestep(cells, obst, density, accel, omega)
+        assert np.array_equal(ra.view(np.uint32), oa.view(np.uint32))
+        assert np.array_equal(rb.view(np.uint32), ob.view(np.uint32))
+        assert np.float32(rav) == np.float32(oav) or (np.isnan(rav) and np.isnan(oav))
+        cells = ob
