@@ -495,7 +495,28 @@ class Grid : public GridBase {
     else if (kernel == LBM_GPU_KERNEL_TMA)
       launch_tma<STRICT, MULTI>(s, a, grid, block, src);
     else
+      launch_vec4<STRICT, MULTI>(s, a, grid, block);
+  }
+  // K1a goes out with programmatic stream serialization (PDL): the next step's grid is
+  // set up while the current one drains, which hides the launch gap on mid-size grids.
+  template <bool STRICT, bool MULTI>
+  void launch_vec4(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block) {
+    static const bool pdl = !(getenv("LBM_GPU_NO_PDL") && getenv("LBM_GPU_NO_PDL")[0] == '1');
+    if (!pdl) {
       lbm::lbm_step_vec4<real, STRICT, MULTI><<<grid, block, 0, s.stream>>>(a);
+      return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, lbm::lbm_step_vec4<real, STRICT, MULTI>, a));
   }
   template <bool STRICT, bool MULTI>
   void launch_tma(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block, int src) {

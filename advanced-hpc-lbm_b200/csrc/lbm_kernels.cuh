@@ -522,6 +522,11 @@ __global__ void __launch_bounds__(LBM_BLOCK_THREADS, (sizeof(real) == 4 ? LBM_MI
 lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   int tx, ty;
   tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  // Programmatic dependent launch: when the host launches the steps with
+  // cudaLaunchAttributeProgrammaticStreamSerialization this grid may be scheduled while
+  // the previous step drains; everything the previous step wrote is visible after this
+  // call.  A no-op for an ordinary launch.
+  cudaGridDependencySynchronize();
   const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
   boundary_wait<real, MULTI>(a, is_boundary);
   const unsigned long long q = vec4_tile<real, STRICT, false>(a, tx, ty);
