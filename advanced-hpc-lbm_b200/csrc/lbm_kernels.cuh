@@ -41,6 +41,9 @@
 #ifndef LBM_AV_MODE
 #define LBM_AV_MODE 0               // 0 block reduction + one atomic per block; 1 = NO av sums (experiment only)
 #endif
+#ifndef LBM_K5_EXPERIMENT
+#define LBM_K5_EXPERIMENT 0         // timing experiments only: 1 = no grid barrier (wrong results), 2 = barrier only
+#endif
 #ifndef LBM_STORE_MODE
 #define LBM_STORE_MODE 0            // 0 plain, 1 st.global.cs (streaming), 2 st.global.cg
 #endif
@@ -794,6 +797,7 @@ lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
     a.push_dn = pa.window + (size_t)((dst * 2 + 1) * 3) * pitch;
     a.av_lo = pa.av_lo + t;
     a.av_hi = pa.av_hi + t;
+#if LBM_K5_EXPERIMENT != 2
     unsigned long long q = 0ULL;
     for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
       const int ty = tile / a.tiles_x;
@@ -801,7 +805,12 @@ lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
       q += (VEC == 4) ? vec4_tile<real, STRICT, true>(a, tx, ty) : scalar_tile<real, STRICT, true>(a, tx, ty);
     }
     block_accumulate(q, a.av_lo, a.av_hi);
+#endif
+#if LBM_K5_EXPERIMENT != 1
+    // (a variant where the last arriver publishes an epoch in a separate word that the
+    // others poll was measured SLOWER -- one more L2 round trip: 128^2 3.0 -> 3.6 us/step)
     grid_barrier(pa.barrier, (unsigned long long)gridDim.x * (unsigned long long)(t + 1));
+#endif
   }
 }
 
