@@ -23,6 +23,10 @@ Two things are built:
    d2q9-bgk_ref          the reference CLI binary, its own flags
    d2q9-bgk_ref_omp      CLI binary of the annotated copy
    d2q9-bgk_ref_f64      CLI binary of the fp64 substitution
+   d2q9-bgk_ref_gpu      the reference with ONLY its step loop (d2q9-bgk.c:180-201) replaced
+                         by the lbm_gpu_* binding of INTEGRATION.md (oracle/reference_binding.inc):
+                         the reference's own initialise / calc_reynolds / write_values around
+                         liblbm_b200.so -- the drop-in demonstration, tests/test_gpu_dropin.py
 """
 import hashlib
 import os
@@ -115,7 +119,32 @@ def build_reference(force=False):
         if not force and _newer(out, REF_SRC, os.path.abspath(__file__)):
             continue
         _gcc_from_sed(sed_args, flags, out)
+    build_dropin(force)
     return OUT_REF
+
+
+def build_dropin(force=False):
+    """The reference's main() with its step loop replaced by the C-ABI binding, linked
+    against the product library (which must have been built already)."""
+    root = os.path.dirname(HERE)
+    pkg = os.path.join(root, "advanced-hpc-lbm_b200")
+    lib = os.path.join(pkg, "liblbm_b200.so")
+    inc = os.path.join(HERE, "reference_binding.inc")
+    out = os.path.join(OUT_REF, "d2q9-bgk_ref_gpu")
+    if not os.path.exists(lib):
+        return None
+    if not force and _newer(out, REF_SRC, inc, lib, os.path.abspath(__file__)):
+        return out
+    sed_args = ["-e", "180,201d", "-e", "179r " + inc, "-e", '57a #include "lbm_gpu.h"']
+    gcc_args = ["-std=c99", "-O2", "-ffp-contract=off", "-I" + os.path.join(root, "include")]
+    sed = subprocess.Popen(["sed"] + sed_args + [REF_SRC], stdout=subprocess.PIPE)
+    try:
+        _run(["gcc"] + gcc_args + ["-x", "c", "-", "-L" + pkg, "-llbm_b200",
+                                   "-Wl,-rpath,$ORIGIN/../../advanced-hpc-lbm_b200", "-lm", "-o", out], stdin=sed.stdout)
+    finally:
+        sed.stdout.close()
+        sed.wait()
+    return out
 
 
 def main():
