@@ -77,7 +77,8 @@ static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large")
 constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
 
 enum SyncWord { kFlagFromBelow = 0, kFlagFromAbove = 1, kBoundaryDone = 2, kScratch0 = 3, kScratch1 = 4,
-                kScratch2 = 5, kGridBarrier = 6, kSyncWords = 8 };
+                kScratch2 = 5, kGridBarrier = 6, kAvScratch = 16 /* kAvWords words */, kSyncWords = 16 + 128 };
+constexpr int kAvWords = LBM_AV_STRIDE * LBM_AV_SLOTS;     // words of one step's |u| sums (1 KiB)
 
 struct GridBase {
   virtual ~GridBase() {}
@@ -101,8 +102,8 @@ struct Slab {
   char* win = nullptr;
   size_t win_bytes = 0, off_sync = 0;
   unsigned long long* sync = nullptr;
-  unsigned long long *av_lo = nullptr, *av_hi = nullptr;
-  size_t av_cap = 0;
+  unsigned long long* av = nullptr;   // per step LBM_AV_SLOTS x {sum of low halves, sum of high halves}
+  size_t av_cap = 0;                  // steps
   void* staging = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -150,7 +151,7 @@ class Grid : public GridBase {
       if (s.stream) cudaStreamSynchronize(s.stream);
       for (int i = 0; i < 2; i++)
         if (s.ipc_mapped[i]) cudaIpcCloseMemHandle(s.ipc_mapped[i]);
-      pool_free(s.av_lo, s);
+      pool_free(s.av, s);
       pool_free(s.staging, s);
       pool_free(s.base, s);
       if (s.stream) cudaStreamSynchronize(s.stream);
@@ -531,15 +532,14 @@ class Grid : public GridBase {
     for (auto& s : slabs) {
       CK(cudaSetDevice(s.device));
       if (s.av_cap < (size_t)n_steps) {
-        pool_free(s.av_lo, s);
-        s.av_lo = nullptr;
+        pool_free(s.av, s);
+        s.av = nullptr;
         s.av_cap = std::max<size_t>((size_t)n_steps, 1024);
         void* av = nullptr;
-        pool_alloc(&av, 2 * s.av_cap * sizeof(unsigned long long), s);
-        s.av_lo = (unsigned long long*)av;
-        s.av_hi = s.av_lo + s.av_cap;
+        pool_alloc(&av, s.av_cap * kAvWords * sizeof(unsigned long long), s);
+        s.av = (unsigned long long*)av;
       }
-      CK(cudaMemsetAsync(s.av_lo, 0, 2 * s.av_cap * sizeof(unsigned long long), s.stream));
+      CK(cudaMemsetAsync(s.av, 0, (size_t)n_steps * kAvWords * sizeof(unsigned long long), s.stream));
     }
     for (auto& s : slabs) { CK(cudaSetDevice(s.device)); CK(cudaEventRecord(s.ev0, s.stream)); }
 
@@ -564,8 +564,7 @@ class Grid : public GridBase {
       a.aw2 = prm.density * prm.accel / (real)36;
       for (int b = 0; b < 2; b++) { pa.lattice[b] = s.lattice[b]; pa.side[b] = s.side[b]; }
       pa.window = (real*)s.win;
-      pa.av_lo = s.av_lo;
-      pa.av_hi = s.av_hi;
+      pa.av = s.av;
       pa.barrier = s.sync + kGridBarrier;
       pa.first_parity = (int)(steps_done & 1);
       pa.n_steps = n_steps;
@@ -598,8 +597,7 @@ class Grid : public GridBase {
         a.side_src = s.side[src];
         a.side_dst = s.side[dst];
         a.mask = s.mask;
-        a.av_lo = s.av_lo + t;
-        a.av_hi = s.av_hi + t;
+        a.av = s.av + (size_t)t * kAvWords;
         a.halo_s = win_section(s.win, src, 0);
         a.halo_n = win_section(s.win, src, 1);
         a.push_up = win_section(s.up_win, dst, 0);
@@ -640,17 +638,19 @@ class Grid : public GridBase {
     steps_done += n_steps;
 
     if (sums_out) {
-      std::vector<unsigned long long> lo(n_steps), hi(n_steps);
+      std::vector<unsigned long long> words((size_t)n_steps * kAvWords);
       std::vector<unsigned __int128> tot(n_steps, 0);
       std::vector<char> bad(n_steps, 0);
       for (auto& s : slabs) {
         CK(cudaSetDevice(s.device));
-        CK(cudaMemcpy(lo.data(), s.av_lo, n_steps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(hi.data(), s.av_hi, n_steps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (int t = 0; t < n_steps; t++) {
-          if (hi[t] & LBM_NONFINITE_MARK) bad[t] = 1;
-          tot[t] += ((unsigned __int128)(hi[t] & ~LBM_NONFINITE_MARK) << 64) | lo[t];
-        }
+        CK(cudaMemcpy(words.data(), s.av, words.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int t = 0; t < n_steps; t++)
+          for (int k = 0; k < LBM_AV_SLOTS; k++) {
+            const unsigned long long lo = words[(size_t)t * kAvWords + LBM_AV_STRIDE * k],
+                                     hi = words[(size_t)t * kAvWords + LBM_AV_STRIDE * k + 1];
+            if (hi & LBM_NONFINITE_MARK) bad[t] = 1;
+            tot[t] += ((unsigned __int128)(hi & ~LBM_NONFINITE_MARK) << 32) + lo;
+          }
       }
       for (int t = 0; t < n_steps; t++)
         sums_out[t] = bad[t] ? std::nan("") : (double)((long double)tot[t] / (long double)LBM_FIX_SCALE);
@@ -712,7 +712,7 @@ class Grid : public GridBase {
       real* d_p = p ? st + 3 * ncells : nullptr;
       lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
           s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, nx, (int)(g - s.row0), n,
-          prm.density, d_ux, d_uy, d_u, d_p, nullptr, nullptr);
+          prm.density, d_ux, d_uy, d_u, d_p, nullptr);
       CK(cudaGetLastError());
       launches++;
       const size_t off = (size_t)(g - row0) * nx;
@@ -730,19 +730,19 @@ class Grid : public GridBase {
     unsigned __int128 tot = 0;
     for (auto& s : slabs) {
       CK(cudaSetDevice(s.device));
-      unsigned long long* lo = s.sync + kScratch1;
-      unsigned long long* hi = s.sync + kScratch2;
-      CK(cudaMemsetAsync(lo, 0, 2 * sizeof(unsigned long long), s.stream));
+      unsigned long long* av = s.sync + kAvScratch;       // 128-byte aligned inside the sync block
+      CK(cudaMemsetAsync(av, 0, kAvWords * sizeof(unsigned long long), s.stream));
       const long long ncells = (long long)s.rows * prm.nx;
       lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
           s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, prm.nx, 0, s.rows, prm.density,
-          nullptr, nullptr, nullptr, nullptr, lo, hi);
+          nullptr, nullptr, nullptr, nullptr, av);
       CK(cudaGetLastError());
       launches++;
-      unsigned long long w[2];
-      CK(cudaMemcpyAsync(w, lo, sizeof w, cudaMemcpyDeviceToHost, s.stream));
+      unsigned long long w[kAvWords];
+      CK(cudaMemcpyAsync(w, av, sizeof w, cudaMemcpyDeviceToHost, s.stream));
       CK(cudaStreamSynchronize(s.stream));
-      tot += ((unsigned __int128)w[1] << 64) | w[0];
+      for (int k = 0; k < LBM_AV_SLOTS; k++)
+        tot += ((unsigned __int128)w[LBM_AV_STRIDE * k + 1] << 32) + w[LBM_AV_STRIDE * k];
     }
     return (double)((long double)tot / (long double)LBM_FIX_SCALE);
   }

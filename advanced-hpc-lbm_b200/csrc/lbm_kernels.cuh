@@ -236,8 +236,7 @@ struct StepArgs {
   const real* side_src;        // accelerated row ny-2, planes {1,3,5,6,7,8} x pitch (read)
   real* side_dst;              // same, written for the next step
   const uint32_t* mask;        // rows x mask_pitch words
-  unsigned long long* av_lo;   // this step's 128-bit |u| sum, low / high word
-  unsigned long long* av_hi;
+  unsigned long long* av;      // this step's |u| sums: LBM_AV_SLOTS lines of {low halves, high halves, pad}
   // halo rows: 3 x pitch each, see "window" above
   const real* halo_s;          // own window, src parity: speeds {2,5,6} of the row below row 0
   const real* halo_n;          // own window, src parity: speeds {4,7,8} of the row above row rows-1
@@ -319,11 +318,40 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// block-wide exact sum of per-thread fixed-point |u| -> one 128-bit atomic accumulate
-__device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned long long* lo,
-                                                 unsigned long long* hi) {
+// Exact sum of the per-thread fixed-point |u| (unit 2^-52).  The sum of a warp (shuffle
+// tree) or of a block is added to the step's accumulators as two fire-and-forget atomics
+// (RED): the low and the high 32-bit half go to two 64-bit words, so that
+// total = (sum of high halves << 32) + sum of low halves with no carry to propagate and no
+// return value to wait for.  LBM_AV_SLOTS such pairs per step, each in its own 128-byte
+// line: one L2 line takes only about 0.47 G atomics/s (measured).
+//   block_accumulate  one pair of atomics per block (shared memory + __syncthreads): the
+//                     per-step kernels, where a 16384^2 step has 2.1 M warps -- one pair
+//                     per WARP was measured 8 % slower there (L2 atomic traffic);
+//   warp_accumulate   one pair per warp, no barrier: the persistent kernel, few warps and
+//                     a grid barrier right behind (128^2: 3.0 -> 2.6 us per step).
+#define LBM_AV_SLOTS 8
+#define LBM_AV_STRIDE 16                 /* words between slots: one 128-byte line each */
+
+__device__ __forceinline__ void av_add(unsigned long long q, unsigned long long* av_step, const unsigned slot) {
+  unsigned long long* p = av_step + LBM_AV_STRIDE * (slot & (LBM_AV_SLOTS - 1));
+  atomicAdd(p, q & 0xffffffffULL);
+  atomicAdd(p + 1, q >> 32);
+}
+
+__device__ __forceinline__ void warp_accumulate(unsigned long long q, unsigned long long* av_step) {
 #if LBM_AV_MODE == 1
-  if (q == 0xffffffffffffffffULL) *lo = q;   // keeps q alive, never true
+  if (q == 0xffffffffffffffffULL) *av_step = q;   // keeps q alive, never true
+  return;
+#endif
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if ((tid & 31) == 0 && q != 0ULL) av_add(q, av_step, blockIdx.x + (tid >> 5));
+}
+
+__device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned long long* av_step) {
+#if LBM_AV_MODE == 1
+  if (q == 0xffffffffffffffffULL) *av_step = q;   // keeps q alive, never true
   return;
 #endif
   __shared__ unsigned long long warp_sums[32];
@@ -337,10 +365,7 @@ __device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned 
     unsigned long long v = (tid < nwarps) ? warp_sums[tid] : 0ULL;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (tid == 0 && v != 0ULL) {
-      const unsigned long long old = atomicAdd(lo, v);
-      if (old + v < old) atomicAdd(hi, 1ULL);
-    }
+    if (tid == 0 && v != 0ULL) av_add(v, av_step, blockIdx.x);
   }
 }
 
@@ -473,7 +498,7 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
   for (int j = 0; j < 4; j++) {
     const real s = cell_update<real, STRICT>(in[j], (obits >> j) & 1u, a.omega, out[j]);
     q += to_fixed(s);
-    if (active && !(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);   // NaN / blow-up
+    if (active && !(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av + 1, LBM_NONFINITE_MARK);   // NaN / blow-up
   }
 
   if (active) {
@@ -533,7 +558,7 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
   boundary_wait<real, MULTI>(a, is_boundary);
   const unsigned long long q = vec4_tile<real, STRICT, false>(a, tx, ty);
-  block_accumulate(q, a.av_lo, a.av_hi);
+  block_accumulate(q, a.av);
   boundary_signal<real, MULTI>(a, is_boundary);
 }
 
@@ -654,7 +679,7 @@ lbm_step_tma(const __grid_constant__ StepArgs<float> a, const __grid_constant__ 
     for (int j = 0; j < 4; j++) {
       const float s = cell_update<float, STRICT>(in[j], (obits >> j) & 1u, a.omega, out[j]);
       q += to_fixed(s);
-      if (active && !(s < (float)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);
+      if (active && !(s < (float)LBM_SPEED_LIMIT)) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
     }
     if (active) {
       float* d = a.dst + oC + x0;
@@ -667,7 +692,7 @@ lbm_step_tma(const __grid_constant__ StepArgs<float> a, const __grid_constant__ 
       q = 0ULL;
     }
   }
-  block_accumulate(q, a.av_lo, a.av_hi);
+  block_accumulate(q, a.av);
   boundary_signal<float, MULTI>(a, is_boundary);
 }
 
@@ -702,7 +727,7 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
     const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
     const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
     q = to_fixed(s);
-    if (!(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av_hi, LBM_NONFINITE_MARK);
+    if (!(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
 #pragma unroll
     for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
     if (cA) {
@@ -734,7 +759,7 @@ lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
   const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
   boundary_wait<real, MULTI>(a, is_boundary);
   const unsigned long long q = scalar_tile<real, STRICT, false>(a, tx, ty);
-  block_accumulate(q, a.av_lo, a.av_hi);
+  block_accumulate(q, a.av);
   boundary_signal<real, MULTI>(a, is_boundary);
 }
 
@@ -755,8 +780,7 @@ struct PersistArgs {
   real* lattice[2];
   real* side[2];
   real* window;                // own window: section (parity b, direction d) at ((b*2+d)*3)*pitch
-  unsigned long long* av_lo;   // n_steps entries
-  unsigned long long* av_hi;
+  unsigned long long* av;      // n_steps x LBM_AV_SLOTS x LBM_AV_STRIDE words
   unsigned long long* barrier; // zeroed before the launch
   int first_parity;            // buffer index read by the first step
   int n_steps;
@@ -795,8 +819,7 @@ lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
     a.halo_n = pa.window + (size_t)((src * 2 + 1) * 3) * pitch;
     a.push_up = pa.window + (size_t)((dst * 2 + 0) * 3) * pitch;
     a.push_dn = pa.window + (size_t)((dst * 2 + 1) * 3) * pitch;
-    a.av_lo = pa.av_lo + t;
-    a.av_hi = pa.av_hi + t;
+    a.av = pa.av + (size_t)t * (LBM_AV_STRIDE * LBM_AV_SLOTS);
 #if LBM_K5_EXPERIMENT != 2
     unsigned long long q = 0ULL;
     for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
@@ -804,7 +827,7 @@ lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
       const int tx = tile - ty * a.tiles_x;
       q += (VEC == 4) ? vec4_tile<real, STRICT, true>(a, tx, ty) : scalar_tile<real, STRICT, true>(a, tx, ty);
     }
-    block_accumulate(q, a.av_lo, a.av_hi);
+    warp_accumulate(q, a.av);
 #endif
 #if LBM_K5_EXPERIMENT != 1
     // (a variant where the last arriver publishes an epoch in a separate word that the
@@ -942,13 +965,13 @@ __global__ void lbm_copy_mask_bits(const uint32_t* __restrict__ in, uint32_t* __
 
 // write_values' per-cell fields (d2q9-bgk.c:2937-2976) for local rows [r0, r0+nrows):
 // dense nx-wide outputs.  Also usable as av_velocity (d2q9-bgk.c:2665-2714) through
-// the 128-bit accumulator when av_lo != NULL.
+// the |u| accumulator (warp_accumulate) when av != NULL.
 template <typename real>
 __global__ void lbm_fields(const real* __restrict__ buf, const uint32_t* __restrict__ mask,
                            long long plane_stride, int pitch, int mask_pitch, int nx, int r0, int nrows,
                            real density, real* __restrict__ ux_out, real* __restrict__ uy_out,
                            real* __restrict__ u_out, real* __restrict__ p_out,
-                           unsigned long long* av_lo, unsigned long long* av_hi) {
+                           unsigned long long* av) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long q = 0ULL;
   if (n < (long long)nrows * nx) {
@@ -970,7 +993,7 @@ __global__ void lbm_fields(const real* __restrict__ buf, const uint32_t* __restr
     if (p_out) p_out[n] = pr;
     q = to_fixed(u);
   }
-  if (av_lo) block_accumulate(q, av_lo, av_hi);
+  if (av) warp_accumulate(q, av);
 }
 
 // Digest of the lattice rows [r0, r0+nrows): two wrapping 64-bit integer sums, so they

@@ -11,9 +11,10 @@ PKG = os.path.join(ROOT, "advanced-hpc-lbm_b200")
 OUT = os.path.join(PKG, "variants")
 VARIANTS = {
     "base": [],
-    "t256_mb4": ["-DLBM_BLOCK_THREADS=256", "-DLBM_MIN_BLOCKS=4", "-DLBM_PERSIST_MIN_BLOCKS=3"],
-    "t256_mb3": ["-DLBM_BLOCK_THREADS=256", "-DLBM_MIN_BLOCKS=3", "-DLBM_PERSIST_MIN_BLOCKS=3"],
-    "t128_mb8": ["-DLBM_BLOCK_THREADS=128", "-DLBM_MIN_BLOCKS=8"],
+    "noav": ["-DLBM_AV_MODE=1"],
+    "t96_mb9": ["-DLBM_BLOCK_THREADS=96", "-DLBM_MIN_BLOCKS=9"],
+    "t160_mb5": ["-DLBM_BLOCK_THREADS=160", "-DLBM_MIN_BLOCKS=5"],
+    "t192_mb4": ["-DLBM_BLOCK_THREADS=192", "-DLBM_MIN_BLOCKS=4"],
 }
 
 
@@ -33,8 +34,9 @@ def build():
 def run():
     for name in VARIANTS:
         env = dict(os.environ, LBM_B200_LIB=os.path.join(OUT, "liblbm_%s.so" % name))
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py"), "--steps", "40",
-                            "--reps", "3", "--kernel", "vec4"], env=env, stdout=subprocess.PIPE, text=True)
+        args = sys.argv[sys.argv.index("--run") + 1:] or ["--steps", "40", "--reps", "3", "--kernel", "vec4"]
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py"), *args], env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         lines = [l for l in r.stdout.splitlines() if "MLUPS" in l]
         print("%-14s %s" % (name, lines[-1] if lines else r.stdout[-300:]), flush=True)
 
