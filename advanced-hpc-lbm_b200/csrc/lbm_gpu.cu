@@ -79,6 +79,7 @@ constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
 enum SyncWord { kFlagFromBelow = 0, kFlagFromAbove = 1, kBoundaryDone = 2, kScratch0 = 3, kScratch1 = 4,
                 kScratch2 = 5, kGridBarrier = 6, kAvScratch = 16 /* kAvWords words */, kSyncWords = 16 + 128 };
 constexpr int kAvWords = LBM_AV_STRIDE * LBM_AV_SLOTS;     // words of one step's |u| sums (1 KiB)
+constexpr int kMaxSegmentSteps = 1 << 16;                  // 64 MiB of sums per run segment
 
 struct GridBase {
   virtual ~GridBase() {}
@@ -525,8 +526,24 @@ class Grid : public GridBase {
       lbm::lbm_step_tma<STRICT, MULTI><<<grid, block, 0, s.stream>>>(a, s.tmap[src], s.tmap_halo[src]);
   }
 
+  // The per-step sums take 1 KiB of device memory per step, so very long runs are cut into
+  // segments of kMaxSegmentSteps (one sync + one read-back per segment, no other effect).
   void run(int n_steps, double* sums_out) {
     if (!connected) throw CudaError{"lattice is not connected to its neighbours yet"};
+    double ms = 0.0;
+    const int total = n_steps;
+    for (int done = 0; done < total; done += kMaxSegmentSteps) {
+      const int n = std::min(kMaxSegmentSteps, total - done);
+      run_segment(n, sums_out ? sums_out + done : nullptr);
+      ms += last_run_ms;
+    }
+    if (total > 0) {
+      last_run_ms = ms;
+      last_step_ms = ms / total;
+    }
+  }
+
+  void run_segment(int n_steps, double* sums_out) {
     if (n_steps <= 0) return;
     const bool strict = (flags & LBM_GPU_STRICT) != 0;
     for (auto& s : slabs) {

@@ -95,6 +95,20 @@ def test_chunked_runs_equal_one_run(kernel):
     assert np.array_equal(av_all, av_parts)
 
 
+def test_long_runs_are_segmented_transparently():
+    """More steps than one run segment (65536): same av_vels and lattice as several calls."""
+    nx, ny, steps = 32, 8, 70000
+    cells, obst = O.random_lattice(nx, ny, seed=19, p_obst=0.05)
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst) as lat:
+        av = lat.run(steps)
+        one = lat.download()
+    with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst) as lat:
+        parts = np.concatenate([lat.run(30000), lat.run(40000)])
+        two = lat.download()
+    assert av.shape == (steps,) and np.array_equal(av, parts) and np.array_equal(one, two)
+    assert np.all(np.isfinite(av))
+
+
 def test_kernel_selection():
     """Small single-GPU grids take the persistent kernel, big ones one launch per step,
     widths that are not a multiple of 4 the scalar kernel; all give the same bits."""
