@@ -104,6 +104,7 @@ struct Slab {
   size_t win_bytes = 0, off_sync = 0;
   unsigned long long* sync = nullptr;
   unsigned long long* av = nullptr;   // per step LBM_AV_SLOTS x {sum of low halves, sum of high halves}
+  unsigned long long* av_compact = nullptr;
   size_t av_cap = 0;                  // steps
   void* staging = nullptr;
   cudaStream_t stream = nullptr;
@@ -553,8 +554,9 @@ class Grid : public GridBase {
         s.av = nullptr;
         s.av_cap = std::max<size_t>((size_t)n_steps, 1024);
         void* av = nullptr;
-        pool_alloc(&av, s.av_cap * kAvWords * sizeof(unsigned long long), s);
+        pool_alloc(&av, s.av_cap * (kAvWords + 2) * sizeof(unsigned long long), s);
         s.av = (unsigned long long*)av;
+        s.av_compact = s.av + s.av_cap * kAvWords;      // {low, high} per step, filled after the run
       }
       CK(cudaMemsetAsync(s.av, 0, (size_t)n_steps * kAvWords * sizeof(unsigned long long), s.stream));
     }
@@ -655,19 +657,22 @@ class Grid : public GridBase {
     steps_done += n_steps;
 
     if (sums_out) {
-      std::vector<unsigned long long> words((size_t)n_steps * kAvWords);
+      std::vector<unsigned long long> words((size_t)n_steps * 2);
       std::vector<unsigned __int128> tot(n_steps, 0);
       std::vector<char> bad(n_steps, 0);
       for (auto& s : slabs) {
         CK(cudaSetDevice(s.device));
-        CK(cudaMemcpy(words.data(), s.av, words.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (int t = 0; t < n_steps; t++)
-          for (int k = 0; k < LBM_AV_SLOTS; k++) {
-            const unsigned long long lo = words[(size_t)t * kAvWords + LBM_AV_STRIDE * k],
-                                     hi = words[(size_t)t * kAvWords + LBM_AV_STRIDE * k + 1];
-            if (hi & LBM_NONFINITE_MARK) bad[t] = 1;
-            tot[t] += ((unsigned __int128)(hi & ~LBM_NONFINITE_MARK) << 32) + lo;
-          }
+        lbm::lbm_compact_av<<<(n_steps + 255) / 256, 256, 0, s.stream>>>(s.av, s.av_compact, n_steps);
+        CK(cudaGetLastError());
+        launches++;
+        CK(cudaMemcpyAsync(words.data(), s.av_compact, words.size() * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        for (int t = 0; t < n_steps; t++) {
+          const unsigned long long lo = words[2 * (size_t)t], hi = words[2 * (size_t)t + 1];
+          if (hi & LBM_NONFINITE_MARK) bad[t] = 1;
+          tot[t] += ((unsigned __int128)(hi & ~LBM_NONFINITE_MARK) << 32) + lo;
+        }
       }
       for (int t = 0; t < n_steps; t++)
         sums_out[t] = bad[t] ? std::nan("") : (double)((long double)tot[t] / (long double)LBM_FIX_SCALE);

@@ -369,6 +369,26 @@ __device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned 
   }
 }
 
+// After a run: fold the LBM_AV_SLOTS padded slots of every step into one {low, high} pair,
+// so that 16 bytes per step cross PCIe instead of 1 KiB.  The non-finite mark (bit 63 of a
+// high word) is OR-ed, everything else summed.
+__global__ void lbm_compact_av(const unsigned long long* __restrict__ av, unsigned long long* __restrict__ out,
+                               int n_steps) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_steps) return;
+  const unsigned long long* p = av + (size_t)t * (LBM_AV_STRIDE * LBM_AV_SLOTS);
+  unsigned long long lo = 0ULL, hi = 0ULL, mark = 0ULL;
+#pragma unroll
+  for (int k = 0; k < LBM_AV_SLOTS; k++) {
+    lo += p[LBM_AV_STRIDE * k];
+    const unsigned long long h = p[LBM_AV_STRIDE * k + 1];
+    hi += h & ~LBM_NONFINITE_MARK;
+    mark |= h & LBM_NONFINITE_MARK;
+  }
+  out[2 * t] = lo;
+  out[2 * t + 1] = hi | mark;
+}
+
 // Block -> tile mapping.  The row tiles that touch the slab's first and last row are
 // given the lowest block indices so that they are dispatched first: their halo pushes
 // leave early and the neighbours' next step never waits for them.
