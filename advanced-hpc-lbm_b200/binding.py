@@ -24,6 +24,7 @@ KERNEL_VEC4 = 16
 SYNC_FLAGS = 32
 KERNEL_PERSISTENT = 64
 POOL = 128
+KERNEL_CLUSTER = 256
 IPC_DESC_BYTES = 256
 
 

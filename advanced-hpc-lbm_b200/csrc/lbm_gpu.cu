@@ -5,6 +5,7 @@
 // CPU fallback: every entry point either runs the CUDA path or returns an error.
 #include "lbm_gpu.h"
 #include "lbm_kernels.cuh"
+#include "lbm_cluster.cuh"
 
 #include <unistd.h>
 
@@ -134,6 +135,9 @@ class Grid : public GridBase {
   unsigned flags = 0;
   int kernel = 0;
   int persistent_vec = 4;      // cells per thread of the persistent kernel (4, or 1 for tiny grids)
+  int cluster_ctas = 0;        // K6: CTAs of the cluster (16 or 8), 0 = not applicable
+  int cluster_rows = 0;        // K6: rows per CTA
+  size_t cluster_smem = 0;     // K6: dynamic shared memory per CTA
   int pitch = 0, mask_pitch = 0;
   bool slab_mode = false;      // one process per GPU: neighbours are other processes
   bool connected = false;      // neighbour views are set
@@ -297,6 +301,7 @@ class Grid : public GridBase {
     if (flags & LBM_GPU_KERNEL_SCALAR) kernel = LBM_GPU_KERNEL_SCALAR;
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
+    else if (flags & LBM_GPU_KERNEL_CLUSTER) kernel = LBM_GPU_KERNEL_VEC4;     // decided in choose_kernel()
     else kernel = LBM_GPU_KERNEL_VEC4;                         // refined in choose_kernel()
     if (flags & LBM_GPU_KERNEL_TMA) {
       if (sizeof(real) != 4) throw CudaError{"the TMA kernel is built for single precision only"};
@@ -331,9 +336,58 @@ class Grid : public GridBase {
 
   // After the slabs exist: grids small enough to be launch-latency bound (they live in
   // L2) run all their steps in one persistent cooperative kernel.
+  const void* cluster_fn() const {
+    return (flags & LBM_GPU_STRICT) ? (const void*)lbm::lbm_steps_cluster<true> : (const void*)lbm::lbm_steps_cluster<false>;
+  }
+
+  // K6 applies to a single fp32 slab whose double-buffered lattice fits in the shared memory
+  // of one cluster (16 CTAs if the device schedules such a cluster, else 8).
+  bool cluster_fits() {
+    if (sizeof(real) != 4 || slabs.size() != 1 || slab_mode) return false;
+    Slab<real>& s = slabs[0];
+    CK(cudaSetDevice(s.device));
+    int max_smem = 0;
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s.device));
+    for (int c : {16, 8}) {
+      const int rows = (s.rows + c - 1) / c;
+      const size_t smem = (size_t)2 * 9 * rows * prm.nx * sizeof(float);
+      if (smem > (size_t)max_smem) continue;
+      if (cudaFuncSetAttribute(cluster_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+          cudaFuncSetAttribute(cluster_fn(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(c);
+      cfg.blockDim = dim3(LBM_CLUSTER_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, cluster_fn(), &cfg) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      cluster_ctas = c;
+      cluster_rows = rows;
+      cluster_smem = smem;
+      return true;
+    }
+    return false;
+  }
+
   void choose_kernel() {
     const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT |
-                                 LBM_GPU_KERNEL_TMA);
+                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER);
+    // K6 is opt-in only: 16 SMs doing all the arithmetic are no faster than K5 spreading it
+    // over the whole chip (profiles/r01_small_grids.md).
+    if (flags & LBM_GPU_KERNEL_CLUSTER) {
+      if (cluster_fits()) { kernel = LBM_GPU_KERNEL_CLUSTER; return; }
+      throw CudaError{"the cluster kernel needs a single-GPU fp32 lattice that fits in one cluster's shared memory"};
+    }
     const bool want = (kernel == LBM_GPU_KERNEL_PERSISTENT);
     if (!want && (forced || slabs.size() != 1 || slab_mode)) return;
     if (slabs.size() != 1 || slab_mode) throw CudaError{"the persistent kernel handles a single slab only"};
@@ -527,6 +581,39 @@ class Grid : public GridBase {
       lbm::lbm_step_tma<STRICT, MULTI><<<grid, block, 0, s.stream>>>(a, s.tmap[src], s.tmap_halo[src]);
   }
 
+  void launch_cluster(int n_steps, bool strict) {
+    if constexpr (sizeof(real) == 4) {
+      Slab<real>& s = slabs[0];
+      CK(cudaSetDevice(s.device));
+      lbm::ClusterArgs a;
+      a.src = s.lattice[steps_done & 1];
+      a.dst = s.lattice[(steps_done + n_steps) & 1];
+      a.mask = s.mask;
+      a.av = s.av;
+      a.plane_stride = plane_stride(s);
+      a.nx = prm.nx; a.ny = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch;
+      a.rows_per_cta = cluster_rows;
+      a.n_steps = n_steps;
+      a.omega = prm.omega;
+      a.aw1 = prm.density * prm.accel / 9.f;
+      a.aw2 = prm.density * prm.accel / 36.f;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cluster_ctas);
+      cfg.blockDim = dim3(LBM_CLUSTER_THREADS);
+      cfg.dynamicSmemBytes = cluster_smem;
+      cfg.stream = s.stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cluster_ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (strict) CK(cudaLaunchKernelEx(&cfg, lbm::lbm_steps_cluster<true>, a));
+      else CK(cudaLaunchKernelEx(&cfg, lbm::lbm_steps_cluster<false>, a));
+      launches++;
+    }
+    (void)n_steps; (void)strict;
+  }
+
   // The per-step sums take 1 KiB of device memory per step, so very long runs are cut into
   // segments of kMaxSegmentSteps (one sync + one read-back per segment, no other effect).
   void run(int n_steps, double* sums_out) {
@@ -566,6 +653,7 @@ class Grid : public GridBase {
     tile_shape(vec, bx, by);
     const int nxv = (prm.nx + vec - 1) / vec;
     const dim3 block(bx, by);
+    if (kernel == LBM_GPU_KERNEL_CLUSTER) launch_cluster(n_steps, strict);
     if (kernel == LBM_GPU_KERNEL_PERSISTENT) {
       Slab<real>& s = slabs[0];
       CK(cudaSetDevice(s.device));
@@ -596,7 +684,7 @@ class Grid : public GridBase {
       CK(cudaLaunchCooperativeKernel(persistent_fn(), dim3(nblocks), block, kargs, 0, s.stream));
       launches++;
     }
-    for (int t = 0; t < n_steps && kernel != LBM_GPU_KERNEL_PERSISTENT; t++) {
+    for (int t = 0; t < n_steps && kernel != LBM_GPU_KERNEL_PERSISTENT && kernel != LBM_GPU_KERNEL_CLUSTER; t++) {
       const unsigned long long step = (unsigned long long)(steps_done + t);
       const int src = (int)(step & 1), dst = src ^ 1;
       const int nslabs = (int)slabs.size();
@@ -655,6 +743,7 @@ class Grid : public GridBase {
     last_run_ms = ms_max;
     last_step_ms = ms_max / n_steps;
     steps_done += n_steps;
+    if (kernel == LBM_GPU_KERNEL_CLUSTER) prepare();      // side row + halo window of the new state
 
     if (sums_out) {
       std::vector<unsigned long long> words((size_t)n_steps * 2);

@@ -69,6 +69,10 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
 #define LBM_GPU_KERNEL_PERSISTENT 64u /* force the persistent cooperative kernel (all steps of a run
                                       in one launch; single GPU).  Chosen by default
                                       for grids small enough to live in L2 */
+#define LBM_GPU_KERNEL_CLUSTER 256u /* force the thread-block-cluster kernel: the lattice lives in the
+                                      distributed shared memory of one cluster for the whole run (single
+                                      GPU, fp32, at most ~48 k cells).  Measured no faster than the persistent kernel, never
+                                      chosen by default */
 #define LBM_GPU_POOL         128u  /* take the lattice from the device's stream-ordered memory pool and
                                       leave it there on destroy: a host that creates many lattices in
                                       one process (sweeps) skips cudaMalloc/cudaFree of ~20 GB each time */

@@ -27,8 +27,18 @@ SHAPES = [
 ODD_SHAPES = [(1, 2), (2, 3), (3, 5), (5, 4), (37, 11), (129, 4), (250, 9), (33, 2), (127, 3), (130, 5), (515, 4)]
 
 
-def _kernels_for(nx):
-    return [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4, L.KERNEL_TMA]
+def cluster_fits(nx, ny):
+    """K6 keeps the double-buffered lattice in the shared memory of one 16-CTA cluster."""
+    return 2 * 9 * ((ny + 15) // 16) * nx * 4 <= 227 * 1024
+
+
+def _kernels_for(nx, ny=None, f64=False):
+    ks = [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4]
+    if not f64:
+        ks.append(L.KERNEL_TMA)
+        if ny is not None and cluster_fits(nx, ny):
+            ks.append(L.KERNEL_CLUSTER)
+    return ks
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES + ODD_SHAPES)
@@ -36,7 +46,7 @@ def _kernels_for(nx):
 def test_strict_bit_exact(nx, ny, steps):
     cells, obst = O.random_lattice(nx, ny, seed=nx * 1000 + ny)
     ref, av_ref, av_ref_d = O.run(cells, obst, steps, DENSITY, ACCEL, OMEGA)
-    for k in _kernels_for(nx):
+    for k in _kernels_for(nx, ny):
         with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=L.STRICT | k) as lat:
             av = lat.run(steps)
             got = lat.download()
@@ -50,7 +60,7 @@ def test_fast_kernel_tolerance(nx, ny):
     steps = 50
     cells, obst = O.random_lattice(nx, ny, seed=7)
     ref, _, av_ref_d = O.run(cells, obst, steps, DENSITY, ACCEL, OMEGA)
-    for k in _kernels_for(nx):
+    for k in _kernels_for(nx, ny):
         with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
             av = lat.run(steps)
             got = lat.download()
@@ -79,10 +89,11 @@ def test_rest_state_and_obstacle_bits():
     assert np.array_equal(b, ref)
 
 
-@pytest.mark.parametrize("kernel", ["vec4", "persistent", "scalar", "tma"])
+@pytest.mark.parametrize("kernel", ["vec4", "persistent", "scalar", "tma", "cluster"])
 def test_chunked_runs_equal_one_run(kernel):
     """run(a); run(b) == run(a+b): no state is lost between calls (odd and even splits)."""
-    k = {"vec4": L.KERNEL_VEC4, "persistent": L.KERNEL_PERSISTENT, "scalar": L.KERNEL_SCALAR, "tma": L.KERNEL_TMA}[kernel]
+    k = {"vec4": L.KERNEL_VEC4, "persistent": L.KERNEL_PERSISTENT, "scalar": L.KERNEL_SCALAR, "tma": L.KERNEL_TMA,
+         "cluster": L.KERNEL_CLUSTER}[kernel]
     nx, ny = 128, 24
     cells, obst = O.random_lattice(nx, ny, seed=11)
     with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
@@ -113,7 +124,9 @@ def test_kernel_selection():
     """Small single-GPU grids take the persistent kernel, big ones one launch per step,
     widths that are not a multiple of 4 the scalar kernel; all give the same bits."""
     with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA) as lat:
-        assert lat.info().kernel == L.KERNEL_PERSISTENT
+        assert lat.info().kernel == L.KERNEL_PERSISTENT          # lives in L2
+    with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_CLUSTER) as lat:
+        assert lat.info().kernel == L.KERNEL_CLUSTER             # opt-in: lives in one cluster's DSMEM
     with L.Lattice(130, 16, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_PERSISTENT          # one cell per thread
     with L.Lattice(4098, 4096, DENSITY, ACCEL, OMEGA) as lat:
@@ -198,7 +211,7 @@ def test_blown_up_lattice_reports_nan_like_the_reference():
     obst[:] = 0
     cells[3, 10, :] = 0.0
     cells[2:5, 9:12, :] = 0.0            # a hole of zero density: pulled values are all zero
-    for k in (L.KERNEL_VEC4, L.KERNEL_SCALAR, L.KERNEL_PERSISTENT):
+    for k in (L.KERNEL_VEC4, L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_TMA, L.KERNEL_CLUSTER):
         with L.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, cells=cells, obstacles=obst, flags=k) as lat:
             av = lat.run(3)
         assert np.isnan(av[0]), (k, av)
@@ -213,8 +226,8 @@ def test_other_parameters_and_the_accelerate_guard(density, accel, omega):
     nx, ny, steps = 132, 9, 4
     cells, obst = O.random_lattice(nx, ny, seed=31, density=density)
     ref, _, av_ref = O.run(cells, obst, steps, density, accel, omega)
-    for k in _kernels_for(nx):
-        for n in ((1, 3) if k != L.KERNEL_PERSISTENT else (1,)):
+    for k in _kernels_for(nx, ny):
+        for n in ((1, 3) if k not in (L.KERNEL_PERSISTENT, L.KERNEL_CLUSTER) else (1,)):
             with L.Lattice(nx, ny, density, accel, omega, cells=cells, obstacles=obst, flags=L.STRICT | k,
                            n_gpus=n, device_ids=[0] * n) as lat:
                 av = lat.run(steps)
@@ -249,6 +262,8 @@ def test_errors_are_reported_not_fatal():
         L.Lattice(8, 1, DENSITY, ACCEL, OMEGA)
     with pytest.raises(L.LbmError, match="single precision only"):
         L.Lattice(16, 4, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_TMA, f64=True)
+    with pytest.raises(L.LbmError, match="fits in one cluster"):
+        L.Lattice(2048, 2048, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_CLUSTER)
     with L.Lattice(8, 4, DENSITY, ACCEL, OMEGA) as lat:
         with pytest.raises(L.LbmError, match="double precision|single precision"):
             L.load_library().lbm_gpu_run_f64(lat.h, 1, None) and L.binding._check(1)

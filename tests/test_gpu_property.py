@@ -11,7 +11,7 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [L.KERNEL_VEC4, L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_TMA]
+KERNELS = [L.KERNEL_VEC4, L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_TMA, L.KERNEL_CLUSTER]
 
 
 @settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large],
@@ -24,7 +24,7 @@ def test_any_configuration_matches_the_oracle(nx, ny, steps, seed, p_obst, kerne
                                               split, walls):
     cells, obst = O.random_lattice(nx, ny, seed=seed, density=density, p_obst=p_obst, walls=walls)
     ref, _, av_ref = O.run(cells, obst, steps, density, accel, omega)
-    n = 1 if kernel == L.KERNEL_PERSISTENT else min(slabs, ny)
+    n = 1 if kernel in (L.KERNEL_PERSISTENT, L.KERNEL_CLUSTER) else min(slabs, ny)
     first = min(split, steps)
     with L.Lattice(nx, ny, density, accel, omega, cells=cells, obstacles=obst, flags=L.STRICT | kernel, n_gpus=n,
                    device_ids=[0] * n) as lat:

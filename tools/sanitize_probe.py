@@ -16,9 +16,9 @@ D, A, W = 0.1, 0.005, 1.85
 for (nx, ny) in [(64, 9), (37, 5), (132, 6)]:
     cells, obst = O.random_lattice(nx, ny, seed=1)
     ref, _, _ = O.run(cells, obst, 4, D, A, W)
-    kernels = [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4]
+    kernels = [L.KERNEL_SCALAR, L.KERNEL_PERSISTENT, L.KERNEL_VEC4, L.KERNEL_TMA, L.KERNEL_CLUSTER]
     for k in kernels:
-        for n in ((1, 3) if k != L.KERNEL_PERSISTENT else (1,)):
+        for n in ((1, 3) if k not in (L.KERNEL_PERSISTENT, L.KERNEL_CLUSTER) else (1,)):
             with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.STRICT | k, n_gpus=n,
                            device_ids=[0] * n) as lat:
                 lat.run(3); lat.run(1)
