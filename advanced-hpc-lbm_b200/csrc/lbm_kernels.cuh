@@ -597,6 +597,8 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
 // ------------------------------------------------------------------------------------
 #define LBM_TMA_TILE (LBM_BLOCK_THREADS * 4)
 #define LBM_TMA_BOX (LBM_TMA_TILE < 256 ? LBM_TMA_TILE : 256)
+static_assert(9 * LBM_TMA_TILE * sizeof(float) + 9 * 32 * sizeof(float) + 16 <= 48 * 1024,
+              "K1c stages its tile in static shared memory: LBM_BLOCK_THREADS must be <= 256");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -11,10 +11,9 @@ PKG = os.path.join(ROOT, "advanced-hpc-lbm_b200")
 OUT = os.path.join(PKG, "variants")
 VARIANTS = {
     "base": [],
-    "noav": ["-DLBM_AV_MODE=1"],
-    "t96_mb9": ["-DLBM_BLOCK_THREADS=96", "-DLBM_MIN_BLOCKS=9"],
-    "t160_mb5": ["-DLBM_BLOCK_THREADS=160", "-DLBM_MIN_BLOCKS=5"],
-    "t192_mb4": ["-DLBM_BLOCK_THREADS=192", "-DLBM_MIN_BLOCKS=4"],
+    "t256": ["-DLBM_BLOCK_THREADS=256", "-DLBM_MIN_BLOCKS=3", "-DLBM_PERSIST_MIN_BLOCKS=3"],
+    "t512": ["-DLBM_BLOCK_THREADS=512", "-DLBM_MIN_BLOCKS=1", "-DLBM_PERSIST_MIN_BLOCKS=1"],
+    "t64": ["-DLBM_BLOCK_THREADS=64", "-DLBM_MIN_BLOCKS=12", "-DLBM_PERSIST_MIN_BLOCKS=12"],
 }
 
 
