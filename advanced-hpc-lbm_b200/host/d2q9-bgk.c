@@ -16,6 +16,7 @@
  *   LBM_SKIP_FINAL_STATE=1 do not write final_state.dat (huge synthetic grids: 16384^2
  *                          would be 24 GB of text)
  *   LBM_REPORT=1           print MLUPS / GB/s / device time after the contract lines
+ *                          (LBM_REPORT=json: the same as one JSON line)
  *   LBM_DEBUG=1            the reference's -DDEBUG output (d2q9-bgk.c:196-200): after every
  *                          timestep print its number, average velocity and total density
  *                          (one lbm_gpu_run + lbm_gpu_digest per step: slow, for eyeballing
@@ -152,7 +153,18 @@ int main(int argc, char* argv[])
   printf("Elapsed Collate time:\t\t\t%.6lf (s)\n", col_toc - col_tic);
   printf("Elapsed Total time:\t\t\t%.6lf (s)\n", tot_toc - tot_tic);
 
-  if (env_flag("LBM_REPORT")) {
+  if (env_flag("LBM_REPORT") && strcmp(getenv("LBM_REPORT"), "json") == 0) {
+    lbm_gpu_info info;
+    GPU(lbm_gpu_get_info(gpu, &info));
+    const double updates = (double)nx * (double)ny * (double)iters;
+    const double dev_s = info.last_run_device_ms * 1e-3;
+    printf("{\"nx\": %d, \"ny\": %d, \"steps\": %d, \"gpus\": %d, \"precision\": \"%s\", \"kernel\": %d, "
+           "\"init_s\": %.6f, \"compute_s\": %.6f, \"collate_s\": %.6f, \"device_compute_s\": %.6f, "
+           "\"mlups_device\": %.1f, \"gbs_72B\": %.1f, \"free_cells\": %lld, \"kernel_launches\": %lld}\n",
+           nx, ny, iters, n_gpus, f64 ? "f64" : "f32", info.kernel, init_toc - init_tic, comp_toc - comp_tic,
+           col_toc - col_tic, dev_s, dev_s > 0 ? updates / dev_s / 1e6 : 0.0, dev_s > 0 ? updates * 72.0 / dev_s / 1e9 : 0.0,
+           info.free_cells, info.kernel_launches);
+  } else if (env_flag("LBM_REPORT")) {
     lbm_gpu_info info;
     GPU(lbm_gpu_get_info(gpu, &info));
     const double updates = (double)nx * (double)ny * (double)iters;
