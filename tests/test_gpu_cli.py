@@ -114,3 +114,14 @@ def test_debug_mode_prints_reference_debug_lines(tmp_path):
     file_avs = np.loadtxt(os.path.join(str(tmp_path), "av_vels.dat"), usecols=[1])
     np.testing.assert_allclose(avs, file_avs, rtol=1e-12)
     assert "==done==" in lines
+
+
+def test_json_report_line(tmp_path):
+    import json
+    out = run_cli("128x128", str(tmp_path), {"LBM_REPORT": "json", "LBM_SKIP_FINAL_STATE": "1"})
+    rep = json.loads(out.strip().splitlines()[-1])
+    assert rep["nx"] == 128 and rep["ny"] == 128 and rep["steps"] == 40000 and rep["gpus"] == 1
+    assert rep["precision"] == "f32" and rep["free_cells"] == 128 * 128 - 508
+    assert rep["mlups_device"] > 100 and abs(rep["gbs_72B"] - rep["mlups_device"] * 72e-3) < 0.2
+    assert not os.path.exists(os.path.join(str(tmp_path), "final_state.dat"))       # LBM_SKIP_FINAL_STATE
+    assert os.path.exists(os.path.join(str(tmp_path), "av_vels.dat"))
