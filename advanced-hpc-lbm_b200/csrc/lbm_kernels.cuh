@@ -44,6 +44,10 @@
 #ifndef LBM_K5_EXPERIMENT
 #define LBM_K5_EXPERIMENT 0         // timing experiments only: 1 = no grid barrier (wrong results), 2 = barrier only
 #endif
+#ifndef LBM_APPROX_MODE
+#define LBM_APPROX_MODE 1           // default (non-strict) fp32 build: 0 = IEEE 1/x and sqrt; 1 = rcp.approx / sqrt.approx
+#endif                              // for |u| of the av sum only (never feeds back into the lattice): -12 % instructions,
+                                    // +4-7 % on L2-resident grids; 2 = also the collision's 1/rho (measured: no further gain)
 #ifndef LBM_STORE_MODE
 #define LBM_STORE_MODE 0            // 0 plain, 1 st.global.cs (streaming), 2 st.global.cg
 #endif
@@ -57,6 +61,24 @@ namespace lbm {
 // contract and uses an algebraically equal, cheaper form of the equilibrium.
 // ------------------------------------------------------------------------------------
 template <typename real, bool STRICT> struct Ops;
+
+// 1/x and sqrt of the default build; the approximate forms are an experiment knob
+__device__ __forceinline__ float fast_rcp(float x, int level) {
+#if LBM_APPROX_MODE >= 1
+  if (LBM_APPROX_MODE >= level) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
+  (void)level;
+  return 1.0f / x;
+}
+__device__ __forceinline__ double fast_rcp(double x, int) { return 1.0 / x; }
+__device__ __forceinline__ float fast_sqrt(float x) {
+#if LBM_APPROX_MODE >= 1
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ double fast_sqrt(double x) { return ::sqrt(x); }
 
 template <> struct Ops<float, true> {
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -160,7 +182,7 @@ __device__ __forceinline__ real cell_update(const real (&p)[9], const bool obsta
     const real n = (p[2] + p[5]) + p[6];
     const real s = (p[4] + p[7]) + p[8];
     const real rho = ((p[0] + p[2]) + (p[4] + e)) + w;
-    const real inv = (real)1 / rho;
+    const real inv = fast_rcp(rho, 2);
     const real ux = (e - w) * inv;
     const real uy = (n - s) * inv;
     const real base = (real)1 - (real)1.5 * (ux * ux + uy * uy);
@@ -183,10 +205,10 @@ __device__ __forceinline__ real cell_update(const real (&p)[9], const bool obsta
     const real n2 = (c[2] + c[5]) + c[6];
     const real s2 = (c[4] + c[7]) + c[8];
     const real rho2 = ((c[0] + c[2]) + (c[4] + e2)) + w_2;
-    const real inv2 = (real)1 / rho2;
+    const real inv2 = fast_rcp(rho2, 1);
     const real vx = (e2 - w_2) * inv2;
     const real vy = (n2 - s2) * inv2;
-    speed = Ops<real, false>::sqrt(vx * vx + vy * vy);
+    speed = fast_sqrt(vx * vx + vy * vy);
   }
   // obstacle: bounce-back of the pulled values (d2q9-bgk.c:971-981), no average
   o[0] = obstacle ? p[0] : c[0];

@@ -11,9 +11,8 @@ PKG = os.path.join(ROOT, "advanced-hpc-lbm_b200")
 OUT = os.path.join(PKG, "variants")
 VARIANTS = {
     "base": [],
-    "t256": ["-DLBM_BLOCK_THREADS=256", "-DLBM_MIN_BLOCKS=3", "-DLBM_PERSIST_MIN_BLOCKS=3"],
-    "t512": ["-DLBM_BLOCK_THREADS=512", "-DLBM_MIN_BLOCKS=1", "-DLBM_PERSIST_MIN_BLOCKS=1"],
-    "t64": ["-DLBM_BLOCK_THREADS=64", "-DLBM_MIN_BLOCKS=12", "-DLBM_PERSIST_MIN_BLOCKS=12"],
+    "approx1": ["-DLBM_APPROX_MODE=1"],
+    "approx2": ["-DLBM_APPROX_MODE=2"],
 }
 
 
