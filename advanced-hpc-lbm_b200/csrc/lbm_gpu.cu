@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -939,6 +940,8 @@ int create_impl(const typename ParamT<real>::type* params, const real* cells_aos
     g->prepare();
   } catch (const CudaError& e) {
     return fail("lbm_gpu_create: %s", e.what.c_str());
+  } catch (const std::exception& e) {      // e.g. std::bad_alloc: never let it cross the C boundary
+    return fail("lbm_gpu_create: %s", e.what());
   }
   *out = reinterpret_cast<lbm_gpu*>(static_cast<GridBase*>(g.release()));
   return 0;
@@ -963,6 +966,8 @@ int guarded(lbm_gpu* h, const char* fn, F&& body) {
     body(*g);
   } catch (const CudaError& e) {
     return fail("%s: %s", fn, e.what.c_str());
+  } catch (const std::exception& e) {
+    return fail("%s: %s", fn, e.what());
   }
   return 0;
 }
@@ -1038,6 +1043,8 @@ int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows
     if (nrows == params->ny) { g->connect_local(); g->prepare(); }   // whole grid in one slab
   } catch (const CudaError& e) {
     return fail("lbm_gpu_create_slab: %s", e.what.c_str());
+  } catch (const std::exception& e) {
+    return fail("lbm_gpu_create_slab: %s", e.what());
   }
   *out = reinterpret_cast<lbm_gpu*>(static_cast<GridBase*>(g.release()));
   return 0;
