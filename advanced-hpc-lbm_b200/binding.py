@@ -25,6 +25,8 @@ SYNC_FLAGS = 32
 KERNEL_PERSISTENT = 64
 POOL = 128
 KERNEL_CLUSTER = 256
+KERNEL_TB2 = 512
+SYNC_EVENTS = 1024
 IPC_DESC_BYTES = 256
 
 
@@ -65,6 +67,7 @@ SYMBOLS = {
                                       C.c_uint, C.POINTER(_P)]),
     "lbm_gpu_ipc_export": (C.c_int, [_P, _P]),
     "lbm_gpu_ipc_connect": (C.c_int, [_P, _P, _P]),
+    "lbm_gpu_ipc_connect_all": (C.c_int, [_P, _P, C.c_int]),
     "lbm_gpu_ipc_prepare": (C.c_int, [_P]),
     "lbm_gpu_run": (C.c_int, [_P, C.c_int, _P]),
     "lbm_gpu_run_f64": (C.c_int, [_P, C.c_int, _P]),
@@ -219,6 +222,11 @@ class Lattice:
         b = np.ascontiguousarray(desc_below, dtype=np.uint8)
         a = np.ascontiguousarray(desc_above, dtype=np.uint8)
         _check(self.lib.lbm_gpu_ipc_connect(self.h, _ptr(b), _ptr(a)))
+
+    def ipc_connect_all(self, descs):
+        """descs: (world, IPC_DESC_BYTES) uint8, the descriptors of ALL ranks in any order."""
+        d = np.ascontiguousarray(descs, dtype=np.uint8).reshape(-1, IPC_DESC_BYTES)
+        _check(self.lib.lbm_gpu_ipc_connect_all(self.h, _ptr(d), int(d.shape[0])))
 
     def ipc_prepare(self):
         _check(self.lib.lbm_gpu_ipc_prepare(self.h))

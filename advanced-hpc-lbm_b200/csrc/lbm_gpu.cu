@@ -6,6 +6,7 @@
 #include "lbm_gpu.h"
 #include "lbm_kernels.cuh"
 #include "lbm_cluster.cuh"
+#include "lbm_tb2.cuh"
 
 #include <unistd.h>
 
@@ -73,7 +74,12 @@ struct IpcDesc {
   unsigned long long win_addr;        // only meaningful inside the exporting process
   unsigned long long win_bytes;
   unsigned long long off_sync;        // byte offset of the sync words inside the window
+  unsigned long long off_gmask;       // byte offset of the ghost mask rows inside the window
   unsigned long long steps_done;
+  unsigned long long passes_done;     // kernel passes so far: the unit of the flag protocol
+  long long local_free_cells;
+  int32_t cur;                        // lattice buffer holding the current state
+  int32_t tb2_ok;                     // this slab could run the two-step kernel
   cudaIpcMemHandle_t handle;          // of the halo window (the lattice itself is never shared)
   char gpu_uuid[16];                  // physical GPU: two flag-ordered slabs must not share one
 };
@@ -81,7 +87,9 @@ static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large")
 constexpr uint32_t kIpcMagic = 0x4c424d31u;   // "LBM1"
 
 enum SyncWord { kFlagFromBelow = 0, kFlagFromAbove = 1, kBoundaryDone = 2, kScratch0 = 3, kScratch1 = 4,
-                kScratch2 = 5, kGridBarrier = 6, kAvScratch = 16 /* kAvWords words */, kSyncWords = 16 + 128 };
+                kScratch2 = 5, kGridBarrier = 6, kAbort = 7, kSyncError = 8 /* must follow kAbort */,
+                kAvScratch = 16 /* kAvWords words */, kSyncWords = 16 + 128 };
+constexpr int kTb2MinRows = 8;                             // per slab, for the two-step kernel
 constexpr int kAvWords = LBM_AV_STRIDE * LBM_AV_SLOTS;     // words of one step's |u| sums (1 KiB)
 constexpr int kMaxSegmentSteps = 1 << 16;                  // 64 MiB of sums per run segment
 
@@ -105,8 +113,9 @@ struct Slab {
   // halo window: [parity 2][direction 2][3 planes][pitch] reals, then the sync words.
   // The only memory neighbours (other GPUs / processes) read or write.
   char* win = nullptr;
-  size_t win_bytes = 0, off_sync = 0;
+  size_t win_bytes = 0, off_sync = 0, off_gmask = 0;
   unsigned long long* sync = nullptr;
+  uint32_t* ghost_mask = nullptr;     // inside the window: mask words of row -1, then of row `rows`
   unsigned long long* av = nullptr;   // per step LBM_AV_SLOTS x {sum of low halves, sum of high halves}
   unsigned long long* av_compact = nullptr;
   size_t av_cap = 0;                  // steps
@@ -120,6 +129,10 @@ struct Slab {
   char* dn_win = nullptr;
   unsigned long long* up_flag = nullptr;      // neighbour above's kFlagFromBelow
   unsigned long long* dn_flag = nullptr;      // neighbour below's kFlagFromAbove
+  unsigned long long* up_abort = nullptr;     // the neighbours' kAbort words
+  unsigned long long* dn_abort = nullptr;
+  uint32_t* up_gmask = nullptr;               // neighbour above's copy of the mask of its row -1
+  uint32_t* dn_gmask = nullptr;               // neighbour below's copy of the mask of its row `rows`
   void* ipc_mapped[2] = {nullptr, nullptr};   // pointers to close on destroy
   bool pooled = false;                        // base/staging came from the stream-ordered pool
   alignas(64) CUtensorMap tmap[2];            // K1c: (x, row, plane) view of lattice[0], lattice[1], row boxes
@@ -148,6 +161,12 @@ class Grid : public GridBase {
   bool use_flags = false;      // cross-slab ordering by device-side flags (else: CUDA events)
   long long global_free_cells = -1;
   long long steps_done = 0;
+  long long passes_done = 0;   // kernel passes (one or two timesteps each): the unit of the flag protocol
+  int cur = 0;                 // lattice buffer / window parity holding the current state (flips per pass)
+  bool tb2 = false;            // two timesteps per pass (K7) wherever two steps remain
+  int tb2_strips = 0, tb2_wout = 0, tb2_seg_rows = 0;
+  bool failed = false;         // a neighbour never arrived: the lattice contents are void
+  unsigned long long timeout_ns = 10000000000ULL;
   long long launches = 0;
   double last_run_ms = 0.0, last_step_ms = 0.0;
   std::vector<Slab<real>> slabs;
@@ -250,9 +269,11 @@ class Grid : public GridBase {
     s.mask = (uint32_t*)(s.base + s.off_mask);
     // the window gets its own allocation, a multiple of 2 MiB so that it never shares a
     // driver block with anything else (it is exported over CUDA IPC)
-    s.off_sync = round_up((size_t)12 * pitch * sizeof(real), 256);
+    s.off_gmask = round_up((size_t)LBM_GHOST_PLANE_ROWS * pitch * sizeof(real), 256);
+    s.off_sync = round_up(s.off_gmask + (size_t)2 * mask_pitch * sizeof(uint32_t), 256);
     s.win_bytes = round_up(s.off_sync + kSyncWords * sizeof(unsigned long long), 2u << 20);
     window_alloc(s);
+    s.ghost_mask = (uint32_t*)(s.win + s.off_gmask);
     s.sync = (unsigned long long*)(s.win + s.off_sync);
     CK(cudaEventCreate(&s.ev0));
     CK(cudaEventCreate(&s.ev1));
@@ -293,17 +314,22 @@ class Grid : public GridBase {
     }
   }
 
-  // window section: parity b, direction d (0 = "from below": speeds 2,5,6; 1 = "from above": 4,7,8)
-  real* win_section(char* win, int b, int d) const { return (real*)win + (size_t)((b * 2 + d) * 3) * pitch; }
+  // ghost rows of a window: parity b, direction d (0 = "from below", 1 = "from above")
+  real* win_section(char* win, int b, int d) const { return (real*)win + lbm::ghost_offset(pitch, b, d); }
 
   long long plane_stride(const Slab<real>& s) const { return (long long)s.rows * pitch; }
 
   void setup_geometry(int nx) {
     pitch = (int)round_up(nx, 32);
     mask_pitch = pitch / 32;
+    if (const char* e = getenv("LBM_GPU_SYNC_TIMEOUT_MS")) {      // longest wait for a neighbouring slab
+      const double ms = atof(e);
+      if (ms > 0) timeout_ns = (unsigned long long)(ms * 1e6);
+    }
     if (flags & LBM_GPU_KERNEL_SCALAR) kernel = LBM_GPU_KERNEL_SCALAR;
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
+    else if (flags & LBM_GPU_KERNEL_TB2) kernel = LBM_GPU_KERNEL_VEC4;         // decided in choose_kernel()
     else if (flags & LBM_GPU_KERNEL_CLUSTER) kernel = LBM_GPU_KERNEL_VEC4;     // decided in choose_kernel()
     else kernel = LBM_GPU_KERNEL_VEC4;                         // refined in choose_kernel()
     if (flags & LBM_GPU_KERNEL_TMA) {
@@ -384,7 +410,7 @@ class Grid : public GridBase {
 
   void choose_kernel() {
     const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT |
-                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER);
+                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER | LBM_GPU_KERNEL_TB2);
     // K6 is opt-in only: 16 SMs doing all the arithmetic are no faster than K5 spreading it
     // over the whole chip (profiles/r01_small_grids.md).
     if (flags & LBM_GPU_KERNEL_CLUSTER) {
@@ -420,6 +446,57 @@ class Grid : public GridBase {
     } else if (!want && tiles > 4LL * cap) {
       kernel = saved;             // large grid: bandwidth bound, one launch per step is free
     }
+  }
+
+  // K7 (two timesteps per pass) needs fp32, a width the 16-byte bulk copies can cut (multiple
+  // of 4, at least one 512-column span), slabs tall enough for two-row ghost zones, and no
+  // kernel forced by the caller.  Every slab of the grid must come to the same answer: the
+  // ghost-row pushes and the flag protocol count passes, not timesteps.
+  bool tb2_possible(int rows_min) const {
+    if (sizeof(real) != 4) return false;
+    if (flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT | LBM_GPU_KERNEL_TMA |
+                 LBM_GPU_KERNEL_CLUSTER)) return false;
+    if (getenv("LBM_GPU_NO_TB2") && getenv("LBM_GPU_NO_TB2")[0] == '1') return false;
+    return (prm.nx % 4 == 0) && prm.nx >= LBM_TB2_SPAN && rows_min >= kTb2MinRows;
+  }
+
+  void enable_tb2() {
+    if constexpr (sizeof(real) == 4) {
+      for (auto& s : slabs) {
+        CK(cudaSetDevice(s.device));
+        for (const void* fn : {(const void*)lbm::lbm_step2_tb<false, false>, (const void*)lbm::lbm_step2_tb<false, true>,
+                               (const void*)lbm::lbm_step2_tb<true, false>, (const void*)lbm::lbm_step2_tb<true, true>})
+          CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lbm::Tb2Smem)));
+      }
+      tb2_strips = (prm.nx + LBM_TB2_MAX_WOUT - 1) / LBM_TB2_MAX_WOUT;
+      tb2_wout = (int)round_up((prm.nx + tb2_strips - 1) / tb2_strips, 4);
+      tb2_seg_rows = 64;
+      if (const char* e = getenv("LBM_TB2_SEG_ROWS")) tb2_seg_rows = std::max(2, atoi(e));   // tuning knob
+      tb2 = true;
+      kernel = LBM_GPU_KERNEL_TB2;
+    }
+  }
+
+  // segments of a slab for K7: equal heights, and the last one keeps at least two rows (the
+  // rows that push into the neighbour above must sit in an edge segment)
+  void tb2_segments(int rows, int& seg_rows, int& nsegs) const {
+    nsegs = std::max(1, (rows + tb2_seg_rows - 1) / tb2_seg_rows);
+    for (;;) {
+      seg_rows = (rows + nsegs - 1) / nsegs;
+      nsegs = (rows + seg_rows - 1) / seg_rows;
+      if (nsegs == 1 || rows - (nsegs - 1) * seg_rows >= 2) return;
+      nsegs--;
+    }
+  }
+
+  // single-process form: decide once all slabs exist
+  void choose_tb2() {
+    int rows_min = slabs[0].rows;
+    for (auto& s : slabs) rows_min = std::min(rows_min, s.rows);
+    const bool want = (flags & LBM_GPU_KERNEL_TB2) != 0;
+    const bool big = (kernel == LBM_GPU_KERNEL_VEC4);        // not taken by the persistent kernel
+    if (tb2_possible(rows_min) && (want || big)) enable_tb2();
+    else if (want) throw CudaError{"the two-step kernel needs fp32, nx a multiple of 4 and >= 512, and >= 8 rows per slab"};
   }
 
   // ------------------------------------------------------------- lattice input ----
@@ -513,21 +590,29 @@ class Grid : public GridBase {
       s.dn_win = dn.win;
       s.up_flag = up.sync + kFlagFromBelow;
       s.dn_flag = dn.sync + kFlagFromAbove;
+      s.up_abort = up.sync + kAbort;
+      s.dn_abort = dn.sync + kAbort;
+      s.up_gmask = up.ghost_mask;
+      s.dn_gmask = dn.ghost_mask + mask_pitch;
     }
     multi = n > 1;
-    use_flags = multi && (flags & LBM_GPU_SYNC_FLAGS);
-    if (use_flags)
-      for (int i = 0; i < n; i++)
-        for (int j = i + 1; j < n; j++)
-          if (slabs[i].device == slabs[j].device)
-            throw CudaError{"LBM_GPU_SYNC_FLAGS needs every slab on its own GPU (kernels that wait on "
-                            "one another must not share a device)"};
+    // Slabs of one process are ordered by the device-side flag protocol (edge blocks wait,
+    // interior blocks never do) whenever every slab has a GPU of its own; slabs that share a
+    // GPU (tests on a one-GPU box) cannot wait on one another inside kernels and are ordered
+    // by CUDA events, as is everything when LBM_GPU_SYNC_EVENTS asks for it.
+    bool distinct = true;
+    for (int i = 0; i < n; i++)
+      for (int j = i + 1; j < n; j++)
+        if (slabs[i].device == slabs[j].device) distinct = false;
+    if ((flags & LBM_GPU_SYNC_FLAGS) && multi && !distinct)
+      throw CudaError{"LBM_GPU_SYNC_FLAGS needs every slab on its own GPU (kernels that wait on "
+                      "one another must not share a device)"};
+    use_flags = multi && distinct && !(flags & LBM_GPU_SYNC_EVENTS);
     connected = true;
   }
 
   void prepare() {
     if (!connected) throw CudaError{"lattice is not connected to its neighbours yet"};
-    const int cur = (int)(steps_done & 1);
     for (auto& s : slabs) {
       CK(cudaSetDevice(s.device));
       lbm::PrepareArgs<real> a;
@@ -536,11 +621,14 @@ class Grid : public GridBase {
       a.mask = s.mask;
       a.push_up = win_section(s.up_win, cur, 0);
       a.push_dn = win_section(s.dn_win, cur, 1);
+      a.mask_up = s.up_gmask;
+      a.mask_dn = s.dn_gmask;
       a.plane_stride = plane_stride(s);
       a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch; a.accel_row = s.accel_row;
+      a.deep = tb2 ? 1 : 0;
       a.aw1 = prm.density * prm.accel / (real)9;      // d2q9-bgk.c:230-231
       a.aw2 = prm.density * prm.accel / (real)36;
-      lbm::lbm_prepare<real><<<(prm.nx + 127) / 128, 128, 0, s.stream>>>(a);
+      lbm::lbm_prepare<real><<<(std::max(prm.nx, mask_pitch) + 127) / 128, 128, 0, s.stream>>>(a);
       CK(cudaGetLastError());
       launches++;
     }
@@ -557,31 +645,39 @@ class Grid : public GridBase {
     else
       launch_vec4<STRICT, MULTI>(s, a, grid, block);
   }
-  // K1a goes out with programmatic stream serialization (PDL): the next step's grid is
-  // set up while the current one drains, which hides the launch gap on mid-size grids.
-  template <bool STRICT, bool MULTI>
-  void launch_vec4(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block) {
+  // Step kernels go out with programmatic stream serialization (PDL): the next pass's grid
+  // is set up while the current one drains, which hides the launch gap on mid-size grids.
+  static bool use_pdl() {
     static const bool pdl = !(getenv("LBM_GPU_NO_PDL") && getenv("LBM_GPU_NO_PDL")[0] == '1');
-    if (!pdl) {
-      lbm::lbm_step_vec4<real, STRICT, MULTI><<<grid, block, 0, s.stream>>>(a);
-      return;
-    }
+    return pdl;
+  }
+  template <typename Kernel, typename Args>
+  void launch_pdl(Slab<real>& s, Kernel k, const Args& a, dim3 grid, dim3 block, size_t smem) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, lbm::lbm_step_vec4<real, STRICT, MULTI>, a));
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, k, a));
+  }
+  template <bool STRICT, bool MULTI>
+  void launch_vec4(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block) {
+    launch_pdl(s, lbm::lbm_step_vec4<real, STRICT, MULTI>, a, grid, block, 0);
   }
   template <bool STRICT, bool MULTI>
   void launch_tma(Slab<real>& s, const lbm::StepArgs<real>& a, dim3 grid, dim3 block, int src) {
     if constexpr (sizeof(real) == 4)
       lbm::lbm_step_tma<STRICT, MULTI><<<grid, block, 0, s.stream>>>(a, s.tmap[src], s.tmap_halo[src]);
+  }
+  template <bool STRICT, bool MULTI>
+  void launch_tb2(Slab<real>& s, const lbm::Tb2Args& ta, dim3 grid) {
+    if constexpr (sizeof(real) == 4)
+      launch_pdl(s, lbm::lbm_step2_tb<STRICT, MULTI>, ta, grid, dim3(LBM_TB2_THREADS), sizeof(lbm::Tb2Smem));
   }
 
   void launch_cluster(int n_steps, bool strict) {
@@ -589,8 +685,8 @@ class Grid : public GridBase {
       Slab<real>& s = slabs[0];
       CK(cudaSetDevice(s.device));
       lbm::ClusterArgs a;
-      a.src = s.lattice[steps_done & 1];
-      a.dst = s.lattice[(steps_done + n_steps) & 1];
+      a.src = s.lattice[cur];
+      a.dst = s.lattice[(cur + n_steps) & 1];
       a.mask = s.mask;
       a.av = s.av;
       a.plane_stride = plane_stride(s);
@@ -621,6 +717,8 @@ class Grid : public GridBase {
   // segments of kMaxSegmentSteps (one sync + one read-back per segment, no other effect).
   void run(int n_steps, double* sums_out) {
     if (!connected) throw CudaError{"lattice is not connected to its neighbours yet"};
+    if (failed) throw CudaError{"an earlier run of this lattice was abandoned (a neighbouring slab never arrived); "
+                                "its contents are void"};
     double ms = 0.0;
     const int total = n_steps;
     for (int done = 0; done < total; done += kMaxSegmentSteps) {
@@ -632,6 +730,95 @@ class Grid : public GridBase {
       last_run_ms = ms;
       last_step_ms = ms / total;
     }
+  }
+
+  // arguments common to every kernel of one pass on one slab: reads buffer `cur`, writes cur^1
+  void fill_step_args(lbm::StepArgs<real>& a, Slab<real>& s, int t_in_segment) {
+    const int src = cur, dst = cur ^ 1;
+    a.src = s.lattice[src];
+    a.dst = s.lattice[dst];
+    a.side_src = s.side[src];
+    a.side_dst = s.side[dst];
+    a.mask = s.mask;
+    a.av = s.av + (size_t)t_in_segment * kAvWords;
+    a.ghost_s = win_section(s.win, src, 0);
+    a.ghost_n = win_section(s.win, src, 1);
+    a.push_up = win_section(s.up_win, dst, 0);
+    a.push_dn = win_section(s.dn_win, dst, 1);
+    a.flag_from_below = s.sync + kFlagFromBelow;
+    a.flag_from_above = s.sync + kFlagFromAbove;
+    a.up_flag = s.up_flag;
+    a.dn_flag = s.dn_flag;
+    a.boundary_done = s.sync + kBoundaryDone;
+    a.abort_word = s.sync + kAbort;
+    a.up_abort = s.up_abort;
+    a.dn_abort = s.dn_abort;
+    a.pass = (unsigned long long)passes_done;
+    a.timeout_ns = timeout_ns;
+    a.plane_stride = plane_stride(s);
+    a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch;
+    a.accel_row = s.accel_row;
+    a.tiles_x = a.tiles_y = 0;
+    a.edge_tiles = 1;
+    a.deep = 0;
+    a.omega = prm.omega;
+    a.aw1 = prm.density * prm.accel / (real)9;       // d2q9-bgk.c:230-231
+    a.aw2 = prm.density * prm.accel / (real)36;
+  }
+
+  // one pass over every slab: one timestep (K1a/K1b/K1c), or two (K7) when `two`
+  void launch_pass(int t_in_segment, int pass_in_segment, bool two) {
+    const bool strict = (flags & LBM_GPU_STRICT) != 0;
+    const int nslabs = (int)slabs.size();
+    int vec, bx, by;
+    tile_shape(vec, bx, by);
+    const int nxv = (prm.nx + vec - 1) / vec;
+    for (int si = 0; si < nslabs; si++) {
+      Slab<real>& s = slabs[si];
+      CK(cudaSetDevice(s.device));
+      if (multi && !use_flags && pass_in_segment > 0) {
+        // slabs sharing a GPU: pass p needs the neighbours' pass p-1 (their pushes into this
+        // slab's ghost rows, and their reads of the ghost rows this pass overwrites)
+        const int up = (si + 1) % nslabs, dn = (si + nslabs - 1) % nslabs;
+        CK(cudaStreamWaitEvent(s.stream, slabs[up].step_ev[(pass_in_segment - 1) & 1], 0));
+        if (dn != up) CK(cudaStreamWaitEvent(s.stream, slabs[dn].step_ev[(pass_in_segment - 1) & 1], 0));
+      }
+      lbm::StepArgs<real> a;
+      fill_step_args(a, s, t_in_segment);
+      if (two) {
+        if constexpr (sizeof(real) == 4) {
+          lbm::Tb2Args ta;
+          int seg_rows, nsegs;
+          tb2_segments(s.rows, seg_rows, nsegs);
+          a.tiles_x = tb2_strips;
+          a.tiles_y = nsegs;
+          a.edge_tiles = 1;
+          a.deep = 1;
+          ta.s = a;
+          ta.ghost_mask = s.ghost_mask;
+          ta.av2 = a.av + kAvWords;
+          ta.wout = tb2_wout;
+          ta.seg_rows = seg_rows;
+          const dim3 grid((unsigned)((long long)tb2_strips * nsegs));
+          if (strict) { if (use_flags) launch_tb2<true, true>(s, ta, grid); else launch_tb2<true, false>(s, ta, grid); }
+          else        { if (use_flags) launch_tb2<false, true>(s, ta, grid); else launch_tb2<false, false>(s, ta, grid); }
+        }
+      } else {
+        a.tiles_x = (nxv + bx - 1) / bx;
+        a.tiles_y = (s.rows + by - 1) / by;
+        a.deep = tb2 ? 1 : 0;                 // a lone step between two-step passes keeps their ghost rows filled
+        a.edge_tiles = tb2 ? 2 : 1;           // (tb2 implies one row per tile: nx >= 512)
+        const dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y));
+        const dim3 block(bx, by);
+        if (strict) { if (use_flags) launch_step<true, true>(s, a, grid, block, cur); else launch_step<true, false>(s, a, grid, block, cur); }
+        else        { if (use_flags) launch_step<false, true>(s, a, grid, block, cur); else launch_step<false, false>(s, a, grid, block, cur); }
+      }
+      CK(cudaGetLastError());
+      launches++;
+      if (multi && !use_flags) CK(cudaEventRecord(s.step_ev[pass_in_segment & 1], s.stream));
+    }
+    passes_done++;
+    cur ^= 1;
   }
 
   void run_segment(int n_steps, double* sums_out) {
@@ -652,31 +839,26 @@ class Grid : public GridBase {
     }
     for (auto& s : slabs) { CK(cudaSetDevice(s.device)); CK(cudaEventRecord(s.ev0, s.stream)); }
 
-    int vec, bx, by;
-    tile_shape(vec, bx, by);
-    const int nxv = (prm.nx + vec - 1) / vec;
-    const dim3 block(bx, by);
-    if (kernel == LBM_GPU_KERNEL_CLUSTER) launch_cluster(n_steps, strict);
-    if (kernel == LBM_GPU_KERNEL_PERSISTENT) {
+    if (kernel == LBM_GPU_KERNEL_CLUSTER) {
+      launch_cluster(n_steps, strict);
+      cur = (cur + n_steps) & 1;
+    } else if (kernel == LBM_GPU_KERNEL_PERSISTENT) {
+      int vec, bx, by;
+      tile_shape(vec, bx, by);
+      const int nxv = (prm.nx + vec - 1) / vec;
       Slab<real>& s = slabs[0];
       CK(cudaSetDevice(s.device));
       lbm::PersistArgs<real> pa;
       memset(&pa, 0, sizeof pa);
+      fill_step_args(pa.s, s, 0);
       lbm::StepArgs<real>& a = pa.s;
-      a.mask = s.mask;
-      a.plane_stride = plane_stride(s);
-      a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch;
-      a.accel_row = s.accel_row;
       a.tiles_x = (nxv + bx - 1) / bx;
       a.tiles_y = (s.rows + by - 1) / by;
-      a.omega = prm.omega;
-      a.aw1 = prm.density * prm.accel / (real)9;
-      a.aw2 = prm.density * prm.accel / (real)36;
       for (int b = 0; b < 2; b++) { pa.lattice[b] = s.lattice[b]; pa.side[b] = s.side[b]; }
       pa.window = (real*)s.win;
       pa.av = s.av;
       pa.barrier = s.sync + kGridBarrier;
-      pa.first_parity = (int)(steps_done & 1);
+      pa.first_parity = cur;
       pa.n_steps = n_steps;
       pa.n_tiles = a.tiles_x * a.tiles_y;
       const int cap = persistent_capacity(s);
@@ -684,54 +866,27 @@ class Grid : public GridBase {
       const int nblocks = (pa.n_tiles + rounds - 1) / rounds;
       CK(cudaMemsetAsync(pa.barrier, 0, sizeof(unsigned long long), s.stream));
       void* kargs[] = {(void*)&pa};
-      CK(cudaLaunchCooperativeKernel(persistent_fn(), dim3(nblocks), block, kargs, 0, s.stream));
+      CK(cudaLaunchCooperativeKernel(persistent_fn(), dim3(nblocks), dim3(bx, by), kargs, 0, s.stream));
       launches++;
-    }
-    for (int t = 0; t < n_steps && kernel != LBM_GPU_KERNEL_PERSISTENT && kernel != LBM_GPU_KERNEL_CLUSTER; t++) {
-      const unsigned long long step = (unsigned long long)(steps_done + t);
-      const int src = (int)(step & 1), dst = src ^ 1;
-      const int nslabs = (int)slabs.size();
-      for (int si = 0; si < nslabs; si++) {
-        Slab<real>& s = slabs[si];
-        CK(cudaSetDevice(s.device));
-        if (multi && !use_flags && t > 0) {
-          // in-process slabs: step t needs the neighbours' step t-1 (their halo pushes
-          // into this slab, and their reads of the ghost rows this step overwrites)
-          const int up = (si + 1) % nslabs, dn = (si + nslabs - 1) % nslabs;
-          CK(cudaStreamWaitEvent(s.stream, slabs[up].step_ev[(t - 1) & 1], 0));
-          if (dn != up) CK(cudaStreamWaitEvent(s.stream, slabs[dn].step_ev[(t - 1) & 1], 0));
+      cur = (cur + n_steps) & 1;
+    } else {
+      int t = 0, p = 0;
+      while (t < n_steps) {
+        const bool two = tb2 && (n_steps - t >= 2);
+        launch_pass(t, p, two);
+        t += two ? 2 : 1;
+        p++;
+      }
+      if (use_flags) {
+        // end of the run: wait (on the device, bounded) until both neighbours are as far
+        for (auto& s : slabs) {
+          CK(cudaSetDevice(s.device));
+          lbm::StepArgs<real> a;
+          fill_step_args(a, s, 0);
+          lbm::lbm_wait_neighbours<real><<<1, 32, 0, s.stream>>>(a);
+          CK(cudaGetLastError());
+          launches++;
         }
-        lbm::StepArgs<real> a;
-        a.src = s.lattice[src];
-        a.dst = s.lattice[dst];
-        a.side_src = s.side[src];
-        a.side_dst = s.side[dst];
-        a.mask = s.mask;
-        a.av = s.av + (size_t)t * kAvWords;
-        a.halo_s = win_section(s.win, src, 0);
-        a.halo_n = win_section(s.win, src, 1);
-        a.push_up = win_section(s.up_win, dst, 0);
-        a.push_dn = win_section(s.dn_win, dst, 1);
-        a.flag_from_below = s.sync + kFlagFromBelow;
-        a.flag_from_above = s.sync + kFlagFromAbove;
-        a.up_flag = s.up_flag;
-        a.dn_flag = s.dn_flag;
-        a.boundary_done = s.sync + kBoundaryDone;
-        a.step = step;
-        a.plane_stride = plane_stride(s);
-        a.nx = prm.nx; a.rows = s.rows; a.pitch = pitch; a.mask_pitch = mask_pitch;
-        a.accel_row = s.accel_row;
-        a.tiles_x = (nxv + bx - 1) / bx;
-        a.tiles_y = (s.rows + by - 1) / by;
-        a.omega = prm.omega;
-        a.aw1 = prm.density * prm.accel / (real)9;
-        a.aw2 = prm.density * prm.accel / (real)36;
-        const dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y));
-        if (strict) { if (use_flags) launch_step<true, true>(s, a, grid, block, src); else launch_step<true, false>(s, a, grid, block, src); }
-        else        { if (use_flags) launch_step<false, true>(s, a, grid, block, src); else launch_step<false, false>(s, a, grid, block, src); }
-        CK(cudaGetLastError());
-        launches++;
-        if (multi && !use_flags) CK(cudaEventRecord(s.step_ev[t & 1], s.stream));
       }
     }
     double ms_max = 0.0;
@@ -746,7 +901,8 @@ class Grid : public GridBase {
     last_run_ms = ms_max;
     last_step_ms = ms_max / n_steps;
     steps_done += n_steps;
-    if (kernel == LBM_GPU_KERNEL_CLUSTER) prepare();      // side row + halo window of the new state
+    if (use_flags) check_sync_errors();
+    if (kernel == LBM_GPU_KERNEL_CLUSTER) prepare();      // side row + ghost rows of the new state
 
     if (sums_out) {
       std::vector<unsigned long long> words((size_t)n_steps * 2);
@@ -771,6 +927,28 @@ class Grid : public GridBase {
     }
   }
 
+  // The flag protocol gave up (see boundary_wait): say why, in the reference's die() spirit.
+  void check_sync_errors() {
+    for (auto& s : slabs) {
+      CK(cudaSetDevice(s.device));
+      unsigned long long w[2] = {0, 0};
+      CK(cudaMemcpyAsync(w, s.sync + kAbort, sizeof w, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+      if (w[0] == 0ULL) continue;
+      failed = true;
+      const unsigned long long why = w[1] >> 56, pass = w[1] & 0xffffffffffffffULL;
+      char msg[256];
+      if (why == LBM_SYNC_TIMEOUT)
+        snprintf(msg, sizeof msg, "rows [%lld,%lld): a neighbouring slab did not complete pass %llu within %.1f s "
+                 "(its process died, or it was asked for a different number of steps); run abandoned",
+                 s.row0, s.row0 + s.rows, pass, (double)timeout_ns * 1e-9);
+      else
+        snprintf(msg, sizeof msg, "rows [%lld,%lld): run abandoned because a neighbouring slab gave up%s",
+                 s.row0, s.row0 + s.rows, why == LBM_SYNC_ABORTED ? " (abort word set)" : "");
+      throw CudaError{msg};
+    }
+  }
+
   long long local_free_cells() const {
     long long n = 0;
     for (auto& s : slabs) n += s.free_cells;
@@ -786,7 +964,6 @@ class Grid : public GridBase {
   }
 
   void download_rows(long long row0, long long nrows, real* out) {
-    const int cur = (int)(steps_done & 1);
     const int nx = prm.nx;
     const size_t row_bytes = (size_t)nx * 9 * sizeof(real);
     if (row_bytes > kStagingBytes) throw CudaError{"nx too large for the AoS staging buffer"};
@@ -809,7 +986,6 @@ class Grid : public GridBase {
   }
 
   void final_fields(long long row0, long long nrows, real* ux, real* uy, real* u, real* p) {
-    const int cur = (int)(steps_done & 1);
     const int nx = prm.nx;
     const size_t row_bytes = (size_t)nx * sizeof(real);
     const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / (4 * row_bytes));
@@ -840,7 +1016,6 @@ class Grid : public GridBase {
   }
 
   double av_velocity_sum() {
-    const int cur = (int)(steps_done & 1);
     unsigned __int128 tot = 0;
     for (auto& s : slabs) {
       CK(cudaSetDevice(s.device));
@@ -863,7 +1038,6 @@ class Grid : public GridBase {
 
   // exact digest of the rows held by this process (see lbm_digest)
   void digest(double* total_density, unsigned long long* checksum) {
-    const int cur = (int)(steps_done & 1);
     unsigned long long mass = 0, sum = 0;
     for (auto& s : slabs) {
       CK(cudaSetDevice(s.device));
@@ -937,6 +1111,7 @@ int create_impl(const typename ParamT<real>::type* params, const real* cells_aos
     }
     g->connect_local();
     g->choose_kernel();
+    g->choose_tb2();
     g->prepare();
   } catch (const CudaError& e) {
     return fail("lbm_gpu_create: %s", e.what.c_str());
@@ -992,7 +1167,7 @@ int run_impl(lbm_gpu* h, int n_steps, real* av_out, double* sums_out, const char
 // ======================================================================= C-ABI ====
 extern "C" {
 
-int lbm_gpu_abi_version(void) { return 1; }
+int lbm_gpu_abi_version(void) { return 2; }
 
 const char* lbm_gpu_last_error(void) { return g_error.c_str(); }
 
@@ -1040,7 +1215,7 @@ int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows
     if (g->kernel == LBM_GPU_KERNEL_TMA) g->make_tensor_maps(s);
     g->load_slab(s, cells_aos_rows, obstacles_rows, 0);
     if (g->kernel == LBM_GPU_KERNEL_PERSISTENT) throw CudaError{"the persistent kernel handles a single slab only"};
-    if (nrows == params->ny) { g->connect_local(); g->prepare(); }   // whole grid in one slab
+    if (nrows == params->ny) { g->connect_local(); g->choose_tb2(); g->prepare(); }   // whole grid in one slab
   } catch (const CudaError& e) {
     return fail("lbm_gpu_create_slab: %s", e.what.c_str());
   } catch (const std::exception& e) {
@@ -1067,7 +1242,12 @@ int lbm_gpu_ipc_export(lbm_gpu* h, void* desc) {
     d.win_addr = (unsigned long long)(uintptr_t)s.win;
     d.win_bytes = s.win_bytes;
     d.off_sync = s.off_sync;
+    d.off_gmask = s.off_gmask;
     d.steps_done = (unsigned long long)g.steps_done;
+    d.passes_done = (unsigned long long)g.passes_done;
+    d.local_free_cells = s.free_cells;
+    d.cur = g.cur;
+    d.tb2_ok = g.tb2_possible(s.rows) ? 1 : 0;
     CK(cudaIpcGetMemHandle(&d.handle, s.win));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, s.device));
@@ -1077,73 +1257,122 @@ int lbm_gpu_ipc_export(lbm_gpu* h, void* desc) {
   });
 }
 
+namespace {
+// wire a one-slab handle to the slabs below and above it; `ring_tb2`: every slab of the ring
+// can run (and therefore will run) the two-step kernel
+void ipc_connect_impl(Grid<float>& g, const IpcDesc& dn, const IpcDesc& up, bool ring_tb2) {
+  if (g.slabs.size() != 1) throw CudaError{"only a one-slab handle can be connected"};
+  Slab<float>& s = g.slabs[0];
+  CK(cudaSetDevice(s.device));
+  const long long ny = g.prm.ny;
+  for (const IpcDesc* d : {&dn, &up}) {
+    if (d->magic != kIpcMagic || d->elem_size != 4) throw CudaError{"bad neighbour descriptor"};
+    if (d->nx != g.prm.nx || d->pitch != g.pitch) throw CudaError{"neighbour descriptor is for another grid width"};
+    if (d->steps_done != (unsigned long long)g.steps_done || d->passes_done != (unsigned long long)g.passes_done ||
+        d->cur != g.cur)
+      throw CudaError{"neighbour is at a different timestep"};
+  }
+  cudaDeviceProp my_prop;
+  CK(cudaGetDeviceProperties(&my_prop, s.device));
+  for (const IpcDesc* d : {&dn, &up})
+    if (memcmp(d->gpu_uuid, my_prop.uuid.bytes, 16) == 0 &&
+        !(d->pid == (int32_t)getpid() && d->win_addr == (unsigned long long)(uintptr_t)s.win))
+      throw CudaError{"a neighbouring slab runs on the same physical GPU: kernels that wait on one another "
+                      "must not share a device (use lbm_gpu_create with n_gpus slabs in one process instead)"};
+  if ((dn.row0 + dn.rows) % ny != s.row0 % ny) throw CudaError{"descriptor 'below' does not hold row0-1"};
+  if ((s.row0 + s.rows) % ny != up.row0 % ny) throw CudaError{"descriptor 'above' does not hold row0+nrows"};
+  auto map = [&](const IpcDesc& d, int slot) -> char* {
+    if (d.pid == (int32_t)getpid()) {
+      // exported by this very process (tests, or a host that drives several GPUs through
+      // slab handles): the address is valid here, no IPC mapping needed
+      char* p = (char*)(uintptr_t)d.win_addr;
+      if (p == s.win) return p;
+      if (d.device == s.device)
+        throw CudaError{"two slabs ordered by device-side flags must not share a GPU"};
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, s.device, d.device));
+      if (!can) throw CudaError{"peer access between the selected GPUs is not available"};
+      cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+      cudaGetLastError();
+      return p;
+    }
+    // LBM_GPU_POOL: the neighbour parks its window in its cache and exports the same
+    // allocation again next time, so the mapping is kept too (cudaIpcCloseMemHandle is
+    // as slow as cudaFree: up to 0.4 s measured)
+    if (g.use_pool()) {
+      std::lock_guard<std::mutex> lock(g_window_mutex);
+      for (auto& c : g_ipc_cache)
+        if (c.device == s.device && memcmp(&c.handle, &d.handle, sizeof d.handle) == 0) return (char*)c.ptr;
+    }
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, d.handle, cudaIpcMemLazyEnablePeerAccess));
+    if (g.use_pool()) {
+      std::lock_guard<std::mutex> lock(g_window_mutex);
+      g_ipc_cache.push_back({d.handle, s.device, p});
+    } else {
+      s.ipc_mapped[slot] = p;
+    }
+    return (char*)p;
+  };
+  for (const IpcDesc* d : {&dn, &up})
+    if (d->win_bytes != s.win_bytes || d->off_sync != s.off_sync || d->off_gmask != s.off_gmask)
+      throw CudaError{"neighbour window layout differs"};
+  s.dn_win = map(dn, 0);
+  s.up_win = (memcmp(&dn.handle, &up.handle, sizeof dn.handle) == 0 && dn.pid == up.pid) ? s.dn_win : map(up, 1);
+  unsigned long long* dn_sync = (unsigned long long*)(s.dn_win + dn.off_sync);
+  unsigned long long* up_sync = (unsigned long long*)(s.up_win + up.off_sync);
+  s.dn_flag = dn_sync + kFlagFromAbove;
+  s.up_flag = up_sync + kFlagFromBelow;
+  s.dn_abort = dn_sync + kAbort;
+  s.up_abort = up_sync + kAbort;
+  s.dn_gmask = (uint32_t*)(s.dn_win + dn.off_gmask) + g.mask_pitch;
+  s.up_gmask = (uint32_t*)(s.up_win + up.off_gmask);
+  g.multi = true;
+  g.use_flags = true;      // neighbours are other processes: device-side flags
+  if (g.flags & LBM_GPU_KERNEL_TB2) {
+    if (!ring_tb2) throw CudaError{"the two-step kernel needs lbm_gpu_ipc_connect_all and fp32, nx a multiple of 4 "
+                                   "and >= 512, >= 8 rows on every rank"};
+  }
+  if (ring_tb2) g.enable_tb2();
+  g.connected = true;
+}
+}  // namespace
+
 int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_above) {
   if (!desc_below || !desc_above) return fail("lbm_gpu_ipc_connect: NULL descriptor");
   return guarded<float>(h, "lbm_gpu_ipc_connect", [&](Grid<float>& g) {
-    if (g.slabs.size() != 1) throw CudaError{"only a one-slab handle can be connected"};
-    Slab<float>& s = g.slabs[0];
-    CK(cudaSetDevice(s.device));
     IpcDesc dn, up;
     memcpy(&dn, desc_below, sizeof dn);
     memcpy(&up, desc_above, sizeof up);
+    ipc_connect_impl(g, dn, up, false);
+  });
+}
+
+int lbm_gpu_ipc_connect_all(lbm_gpu* h, const void* descs, int n) {
+  if (!descs || n < 1) return fail("lbm_gpu_ipc_connect_all: bad argument");
+  return guarded<float>(h, "lbm_gpu_ipc_connect_all", [&](Grid<float>& g) {
+    if (g.slabs.size() != 1) throw CudaError{"only a one-slab handle can be connected"};
+    Slab<float>& s = g.slabs[0];
+    std::vector<IpcDesc> all(n);
+    for (int i = 0; i < n; i++) memcpy(&all[i], (const char*)descs + (size_t)i * LBM_GPU_IPC_DESC_BYTES, sizeof(IpcDesc));
     const long long ny = g.prm.ny;
-    for (const IpcDesc* d : {&dn, &up}) {
-      if (d->magic != kIpcMagic || d->elem_size != 4) throw CudaError{"bad neighbour descriptor"};
-      if (d->nx != g.prm.nx || d->pitch != g.pitch) throw CudaError{"neighbour descriptor is for another grid width"};
-      if (d->steps_done != (unsigned long long)g.steps_done) throw CudaError{"neighbour is at a different timestep"};
+    long long rows_total = 0, free_total = 0;
+    int below = -1, above = -1;
+    bool all_tb2 = true;
+    for (int i = 0; i < n; i++) {
+      const IpcDesc& d = all[i];
+      if (d.magic != kIpcMagic) throw CudaError{"bad descriptor in the list"};
+      rows_total += d.rows;
+      free_total += d.local_free_cells;
+      all_tb2 = all_tb2 && d.tb2_ok && d.rows >= kTb2MinRows;
+      if ((d.row0 + d.rows) % ny == s.row0 % ny) below = i;
+      if ((s.row0 + s.rows) % ny == d.row0 % ny) above = i;
     }
-    cudaDeviceProp my_prop;
-    CK(cudaGetDeviceProperties(&my_prop, s.device));
-    for (const IpcDesc* d : {&dn, &up})
-      if (memcmp(d->gpu_uuid, my_prop.uuid.bytes, 16) == 0 &&
-          !(d->pid == (int32_t)getpid() && d->win_addr == (unsigned long long)(uintptr_t)s.win))
-        throw CudaError{"a neighbouring slab runs on the same physical GPU: kernels that wait on one another "
-                        "must not share a device (use lbm_gpu_create with n_gpus slabs in one process instead)"};
-    if ((dn.row0 + dn.rows) % ny != s.row0 % ny) throw CudaError{"descriptor 'below' does not hold row0-1"};
-    if ((s.row0 + s.rows) % ny != up.row0 % ny) throw CudaError{"descriptor 'above' does not hold row0+nrows"};
-    auto map = [&](const IpcDesc& d, int slot) -> char* {
-      if (d.pid == (int32_t)getpid()) {
-        // exported by this very process (tests, or a host that drives several GPUs through
-        // slab handles): the address is valid here, no IPC mapping needed
-        char* p = (char*)(uintptr_t)d.win_addr;
-        if (p == s.win) return p;
-        if (d.device == s.device)
-          throw CudaError{"two slabs ordered by device-side flags must not share a GPU"};
-        int can = 0;
-        CK(cudaDeviceCanAccessPeer(&can, s.device, d.device));
-        if (!can) throw CudaError{"peer access between the selected GPUs is not available"};
-        cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
-        cudaGetLastError();
-        return p;
-      }
-      // LBM_GPU_POOL: the neighbour parks its window in its cache and exports the same
-      // allocation again next time, so the mapping is kept too (cudaIpcCloseMemHandle is
-      // as slow as cudaFree: up to 0.4 s measured)
-      if (g.use_pool()) {
-        std::lock_guard<std::mutex> lock(g_window_mutex);
-        for (auto& c : g_ipc_cache)
-          if (c.device == s.device && memcmp(&c.handle, &d.handle, sizeof d.handle) == 0) return (char*)c.ptr;
-      }
-      void* p = nullptr;
-      CK(cudaIpcOpenMemHandle(&p, d.handle, cudaIpcMemLazyEnablePeerAccess));
-      if (g.use_pool()) {
-        std::lock_guard<std::mutex> lock(g_window_mutex);
-        g_ipc_cache.push_back({d.handle, s.device, p});
-      } else {
-        s.ipc_mapped[slot] = p;
-      }
-      return (char*)p;
-    };
-    for (const IpcDesc* d : {&dn, &up})
-      if (d->win_bytes != s.win_bytes || d->off_sync != s.off_sync) throw CudaError{"neighbour window layout differs"};
-    s.dn_win = map(dn, 0);
-    s.up_win = (memcmp(&dn.handle, &up.handle, sizeof dn.handle) == 0 && dn.pid == up.pid) ? s.dn_win : map(up, 1);
-    s.dn_flag = (unsigned long long*)(s.dn_win + dn.off_sync) + kFlagFromAbove;
-    s.up_flag = (unsigned long long*)(s.up_win + up.off_sync) + kFlagFromBelow;
-    g.multi = true;
-    g.use_flags = true;      // neighbours are other processes: device-side flags
-    g.connected = true;
+    if (rows_total != ny) throw CudaError{"the descriptors do not cover the grid's rows exactly once"};
+    if (below < 0 || above < 0) throw CudaError{"no descriptor holds the rows next to this slab"};
+    ipc_connect_impl(g, all[below], all[above], all_tb2);
+    g.global_free_cells = free_total;
   });
 }
 
@@ -1225,7 +1454,7 @@ int lbm_gpu_digest(lbm_gpu* h, double* total_density, unsigned long long* checks
 int lbm_gpu_upload(lbm_gpu* h, const float* cells_aos) {
   if (!cells_aos) return fail("lbm_gpu_upload: NULL input");
   return guarded<float>(h, "lbm_gpu_upload", [&](Grid<float>& g) {
-    const int cur = (int)(g.steps_done & 1);
+    const int cur = g.cur;
     const long long base = g.slabs[0].row0;
     for (auto& s : g.slabs) g.upload_cells(s, cells_aos + (size_t)(s.row0 - base) * g.prm.nx * 9, cur);
     if (!g.slab_mode || g.slabs[0].rows == g.prm.ny) g.prepare();
@@ -1234,7 +1463,7 @@ int lbm_gpu_upload(lbm_gpu* h, const float* cells_aos) {
 int lbm_gpu_upload_f64(lbm_gpu* h, const double* cells_aos) {
   if (!cells_aos) return fail("lbm_gpu_upload_f64: NULL input");
   return guarded<double>(h, "lbm_gpu_upload_f64", [&](Grid<double>& g) {
-    const int cur = (int)(g.steps_done & 1);
+    const int cur = g.cur;
     for (auto& s : g.slabs) g.upload_cells(s, cells_aos + (size_t)s.row0 * g.prm.nx * 9, cur);
     g.prepare();
   });

@@ -7,12 +7,15 @@
 //
 // Data layout in HBM (one "slab" = the rows one GPU holds):
 //   lattice  2 buffers x 9 planes x rows x pitch   structure-of-arrays;
-//   window   2 parities x 2 directions x 3 planes x pitch: the halo rows.  "from below"
-//            holds speeds 2,5,6 of the row under the slab's first row, "from above"
-//            speeds 4,7,8 of the row over its last row (periodic in y, so with one slab
-//            they are the slab's own opposite edge rows).  Written by the NEIGHBOURS'
-//            step kernels (peer stores over NVLink), read by this slab's edge rows.  It
-//            is the only memory other GPUs / processes map, together with the flags;
+//   window   ghost rows, 2 parities x 2 directions x 2 depths x 9 planes x pitch.  Direction
+//            "from below" holds the rows under the slab's first row (depth 0 = row -1,
+//            depth 1 = row -2), "from above" the rows over its last row (periodic in y, so
+//            with one slab they are the slab's own opposite edge rows).  Written by the
+//            NEIGHBOURS' step kernels (peer stores over NVLink), read by this slab's edge
+//            rows.  The one-step kernels use speeds 2,5,6 / 4,7,8 of depth 0 only; the
+//            two-step kernel (K7) also needs 0,1,3 of depth 0 and 2,5,6 / 4,7,8 of depth 1.
+//            Behind them: the mask words of rows -1 and `rows`, and the sync words.  The
+//            window is the only memory other GPUs / processes map;
 //   mask     rows x pitch/32 uint32, bit = 1 for an obstacle cell;
 //   side     2 x 6 x pitch: row ny-2 of planes 1,3,5,6,7,8 AFTER accelerate_flow.
 //            The lattice itself always holds the un-accelerated state; readers that
@@ -38,47 +41,49 @@
 #ifndef LBM_PERSIST_MIN_BLOCKS
 #define LBM_PERSIST_MIN_BLOCKS 6    // K5: keeps it at <= 85 registers so 6 blocks/SM are resident
 #endif
+// Timing experiments that produce WRONG results exist only in builds made with
+// -DLBM_EXPERIMENTS (tools/build_variants.py); the shipped library cannot contain them.
+#ifdef LBM_EXPERIMENTS
 #ifndef LBM_AV_MODE
-#define LBM_AV_MODE 0               // 0 block reduction + one atomic per block; 1 = NO av sums (experiment only)
+#define LBM_AV_MODE 0               // 1 = no av sums
 #endif
 #ifndef LBM_K5_EXPERIMENT
-#define LBM_K5_EXPERIMENT 0         // timing experiments only: 1 = no grid barrier (wrong results), 2 = barrier only
+#define LBM_K5_EXPERIMENT 0         // 1 = no grid barrier, 2 = barrier only
 #endif
-#ifndef LBM_APPROX_MODE
-#define LBM_APPROX_MODE 1           // default (non-strict) fp32 build: 0 = IEEE 1/x and sqrt; 1 = rcp.approx / sqrt.approx
-#endif                              // for |u| of the av sum only (never feeds back into the lattice): -12 % instructions,
-                                    // +4-7 % on L2-resident grids; 2 = also the collision's 1/rho (measured: no further gain)
+#else
+#if defined(LBM_AV_MODE) || defined(LBM_K5_EXPERIMENT)
+#error "LBM_AV_MODE / LBM_K5_EXPERIMENT need -DLBM_EXPERIMENTS: they produce wrong results"
+#endif
+#define LBM_AV_MODE 0
+#define LBM_K5_EXPERIMENT 0
+#endif
+static_assert(
+#ifdef LBM_EXPERIMENTS
+    true ||
+#endif
+    (LBM_AV_MODE == 0 && LBM_K5_EXPERIMENT == 0), "the shipped build has every experiment switch off");
 #ifndef LBM_STORE_MODE
 #define LBM_STORE_MODE 0            // 0 plain, 1 st.global.cs (streaming), 2 st.global.cg
 #endif
+#ifndef LBM_PACKED
+#define LBM_PACKED 1                // default fp32 collision: 1 = packed f32x2 lanes (two cells per instruction),
+#endif                              // 0 = the same operation sequence one cell at a time (same bits)
 
 namespace lbm {
 
 // ------------------------------------------------------------------------------------
-// arithmetic policy: STRICT mirrors the reference's C expression trees with
-// round-to-nearest single operations (never contracted into FMA) so the result is
-// bit-identical to a gcc -O2 -ffp-contract=off build; the default lets the compiler
-// contract and uses an algebraically equal, cheaper form of the equilibrium.
+// arithmetic policy.
+//   STRICT   mirrors the reference's C expression trees with round-to-nearest single
+//            operations (never contracted into FMA) so the result is bit-identical to a
+//            gcc -O2 -ffp-contract=off build of d2q9-bgk.c:983-1128.
+//   default  the same maths in an algebraically equal, cheaper form, written ONCE over a
+//            "lane" type with explicit round-to-nearest add / mul / fma (nothing is left
+//            to the compiler's contraction choices): Lane<float2> issues the packed
+//            FADD2 / FMUL2 / FFMA2 of sm_100a -- two cells per instruction -- and
+//            Lane<float> / Lane<double> are the one-cell forms of the SAME operation
+//            sequence, so every kernel variant of one precision produces the same bits.
 // ------------------------------------------------------------------------------------
 template <typename real, bool STRICT> struct Ops;
-
-// 1/x and sqrt of the default build; the approximate forms are an experiment knob
-__device__ __forceinline__ float fast_rcp(float x, int level) {
-#if LBM_APPROX_MODE >= 1
-  if (LBM_APPROX_MODE >= level) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-#endif
-  (void)level;
-  return 1.0f / x;
-}
-__device__ __forceinline__ double fast_rcp(double x, int) { return 1.0 / x; }
-__device__ __forceinline__ float fast_sqrt(float x) {
-#if LBM_APPROX_MODE >= 1
-  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
-#else
-  return sqrtf(x);
-#endif
-}
-__device__ __forceinline__ double fast_sqrt(double x) { return ::sqrt(x); }
 
 template <> struct Ops<float, true> {
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -94,35 +99,142 @@ template <> struct Ops<double, true> {
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
   static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
 };
-template <> struct Ops<float, false> {
-  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
-  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
-  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
-  static __device__ __forceinline__ float div(float a, float b) { return a / b; }
-  static __device__ __forceinline__ float sqrt(float a) { return sqrtf(a); }
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+
+template <typename V> struct Lane;
+template <> struct Lane<float> {
+  typedef float S;
+  static __device__ __forceinline__ float bc(float s) { return s; }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  // -(1/x): hardware reciprocal (1 ulp) of -x plus one Newton step
+  static __device__ __forceinline__ float nrcp(float x) {
+    const float nr = rcp_approx(-x);
+    return __fmaf_rn(nr, __fmaf_rn(x, nr, 1.0f), nr);
+  }
 };
-template <> struct Ops<double, false> {
-  static __device__ __forceinline__ double add(double a, double b) { return a + b; }
-  static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
-  static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
-  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
-  static __device__ __forceinline__ double sqrt(double a) { return ::sqrt(a); }
+template <> struct Lane<double> {
+  typedef double S;
+  static __device__ __forceinline__ double bc(double s) { return s; }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double nrcp(double x) { return __ddiv_rn(-1.0, x); }
 };
+#define LBM_F32X2_OP2(name, ptx)                                                                        \
+  static __device__ __forceinline__ float2 name(float2 a, float2 b) {                                   \
+    float2 d;                                                                                           \
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; " ptx ".rn.f32x2 rd, ra, rb; " \
+        "mov.b64 {%0,%1}, rd;}" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));       \
+    return d;                                                                                           \
+  }
+template <> struct Lane<float2> {
+  typedef float S;
+  static __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+  LBM_F32X2_OP2(add, "add")
+  LBM_F32X2_OP2(sub, "sub")
+  LBM_F32X2_OP2(mul, "mul")
+  static __device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+  }
+  static __device__ __forceinline__ float2 nrcp(float2 x) {
+    const float2 nr = make_float2(rcp_approx(-x.x), rcp_approx(-x.y));
+    return fma(nr, fma(x, nr, make_float2(1.0f, 1.0f)), nr);
+  }
+};
+#undef LBM_F32X2_OP2
+
+// loop-invariant operands of the default collision, broadcast to the lane type once per thread
+template <typename V>
+struct FastConsts {
+  V keep, ow0, ow1, ow2, one, m15, three, mthree, f45;
+  __device__ __forceinline__ explicit FastConsts(const typename Lane<V>::S omega) {
+    typedef typename Lane<V>::S S;
+    typedef Lane<V> L;
+    keep = L::bc((S)1 - omega);
+    ow0 = L::bc(omega * (S)(4.0 / 9.0));
+    ow1 = L::bc(omega * (S)(1.0 / 9.0));
+    ow2 = L::bc(omega * (S)(1.0 / 36.0));
+    one = L::bc((S)1); m15 = L::bc((S)-1.5); three = L::bc((S)3); mthree = L::bc((S)-3); f45 = L::bc((S)4.5);
+  }
+};
+
+// BGK collision (d2q9-bgk.c:983-1100) of one lane of cells, default arithmetic:
+//   c_k = (1 - omega) p_k + omega w_k rho (1 + 3 u_k + 4.5 u_k^2 - 1.5 u^2)
+// with one reciprocal instead of two divisions and 1/c_sq = 3, 1/(2 c_sq^2) = 4.5,
+// 1/(2 c_sq) = 1.5.  Returns u^2 of the PULLED values.  BGK conserves mass and momentum, so
+// this is also u^2 of the stored values (what d2q9-bgk.c:1103-1128 recomputes for the
+// average) up to rounding -- the reference's own collision_and_vel (d2q9-bgk.c:2543) takes
+// the average from the same place.  60 lane operations per call.
+template <typename V>
+__device__ __forceinline__ V collide_fast(const V (&p)[9], const FastConsts<V>& k, V (&c)[9]) {
+  typedef Lane<V> L;
+  const V e = L::add(L::add(p[1], p[5]), p[8]);
+  const V w = L::add(L::add(p[3], p[6]), p[7]);
+  const V n = L::add(L::add(p[2], p[5]), p[6]);
+  const V s = L::add(L::add(p[4], p[7]), p[8]);
+  const V rho = L::add(L::add(L::add(p[0], p[2]), L::add(p[4], e)), w);
+  const V ninv = L::nrcp(rho);
+  const V ux = L::mul(L::sub(w, e), ninv);
+  const V uy = L::mul(L::sub(s, n), ninv);
+  const V usq = L::fma(uy, uy, L::mul(ux, ux));
+  const V base = L::fma(k.m15, usq, k.one);
+  const V r1 = L::mul(rho, k.ow1), r2 = L::mul(rho, k.ow2);
+  const V b0 = L::mul(L::mul(rho, k.ow0), base);
+  const V b1 = L::mul(r1, base), l1 = L::mul(r1, k.three), n1 = L::mul(r1, k.mthree), q1 = L::mul(r1, k.f45);
+  const V b2 = L::mul(r2, base), l2 = L::mul(r2, k.three), n2 = L::mul(r2, k.mthree), q2 = L::mul(r2, k.f45);
+  const V upv = L::add(ux, uy), umv = L::sub(ux, uy);
+  c[0] = L::fma(k.keep, p[0], b0);
+  // omega w rho (base + 3 u + 4.5 u^2) = b + u (l + q u); the opposite direction takes l -> -l
+#define LBM_DIR(kk, u, lin, quad, b) c[kk] = L::fma(k.keep, p[kk], L::fma(u, L::fma(quad, u, lin), b))
+  LBM_DIR(1, ux, l1, q1, b1);  LBM_DIR(3, ux, n1, q1, b1);
+  LBM_DIR(2, uy, l1, q1, b1);  LBM_DIR(4, uy, n1, q1, b1);
+  LBM_DIR(5, upv, l2, q2, b2); LBM_DIR(7, upv, n2, q2, b2);
+  LBM_DIR(8, umv, l2, q2, b2); LBM_DIR(6, umv, n2, q2, b2);
+#undef LBM_DIR
+  return usq;
+}
+
+__device__ __forceinline__ float speed_of(float usq) { return sqrt_approx(usq); }
+__device__ __forceinline__ double speed_of(double usq) { return ::sqrt(usq); }
 
 // |u| is accumulated as an exact 128-bit fixed-point sum (unit 2^-52): integer adds
 // are associative, so the per-step average does not depend on block scheduling, grid
 // shape or on how the rows are split over GPUs.
 #define LBM_FIX_SCALE 4503599627370496.0 /* 2^52 */
-// A cell whose |u| is NaN or beyond any physical value (the lattice has blown up) cannot
-// be represented in the fixed-point sum: the step's high word gets this bit and the host
-// reports that step's average as NaN, which is what the reference's float sum would give.
-#define LBM_SPEED_LIMIT 2048.0
+// A cell whose |u| is NaN or beyond any physical value (the lattice has blown up; the speed
+// of sound is 0.577) cannot be represented in the fixed-point sum: the step's high word gets
+// this bit and the host reports that step's average as NaN, which is what the reference's
+// float sum would give a few steps later at the latest.  The bound also keeps every
+// per-thread partial sum (up to 4 cells x 256 rows) below 2^64; partial sums are split
+// into 32-bit halves before they are added across threads.
+#define LBM_SPEED_LIMIT 2.0
 #define LBM_NONFINITE_MARK (1ULL << 63)
 __device__ __forceinline__ unsigned long long to_fixed(float s) {
   return __float2ull_rn(s * 4503599627370496.0f);
 }
 __device__ __forceinline__ unsigned long long to_fixed(double s) {
   return __double2ull_rn(s * 4503599627370496.0);
+}
+
+// bounce-back of the pulled values (d2q9-bgk.c:971-981)
+template <typename real>
+__device__ __forceinline__ void cell_rebound(const real (&p)[9], real (&o)[9]) {
+  o[0] = p[0]; o[1] = p[3]; o[2] = p[4]; o[3] = p[1]; o[4] = p[2];
+  o[5] = p[7]; o[6] = p[8]; o[7] = p[5]; o[8] = p[6];
 }
 
 // ------------------------------------------------------------------------------------
@@ -132,7 +244,7 @@ __device__ __forceinline__ unsigned long long to_fixed(double s) {
 template <typename real, bool STRICT>
 __device__ __forceinline__ real cell_update(const real (&p)[9], const bool obstacle, const real omega,
                                             real (&o)[9]) {
-  typedef Ops<real, STRICT> M;
+  typedef Ops<real, true> M;
   real c[9];
   real speed;
   if (STRICT) {
@@ -174,53 +286,89 @@ __device__ __forceinline__ real cell_update(const real (&p)[9], const bool obsta
     const real vy = M::div(M::sub(M::add(M::add(c[2], c[5]), c[6]), M::add(M::add(c[4], c[7]), c[8])), rho2);
     speed = M::sqrt(M::add(M::mul(vx, vx), M::mul(vy, vy)));
   } else {
-    // same maths, cheaper form: one reciprocal, 1/c_sq = 3, 1/(2 c_sq^2) = 4.5,
-    // 1/(2 c_sq) = 1.5; the compiler is free to contract into FMA.
-    const real w0 = (real)(4.0 / 9.0), w1 = (real)(1.0 / 9.0), w2 = (real)(1.0 / 36.0);
-    const real e = (p[1] + p[5]) + p[8];
-    const real w = (p[3] + p[6]) + p[7];
-    const real n = (p[2] + p[5]) + p[6];
-    const real s = (p[4] + p[7]) + p[8];
-    const real rho = ((p[0] + p[2]) + (p[4] + e)) + w;
-    const real inv = fast_rcp(rho, 2);
-    const real ux = (e - w) * inv;
-    const real uy = (n - s) * inv;
-    const real base = (real)1 - (real)1.5 * (ux * ux + uy * uy);
-    const real r0 = omega * w0 * rho, r1 = omega * w1 * rho, r2 = omega * w2 * rho;
-    const real keep = (real)1 - omega;
-    const real upv = ux + uy, umv = ux - uy;
-#define LBM_EQ(uk) (base + (uk) * ((real)3 + (real)4.5 * (uk)))
-    c[0] = keep * p[0] + r0 * base;
-    c[1] = keep * p[1] + r1 * LBM_EQ(ux);
-    c[2] = keep * p[2] + r1 * LBM_EQ(uy);
-    c[3] = keep * p[3] + r1 * LBM_EQ(-ux);
-    c[4] = keep * p[4] + r1 * LBM_EQ(-uy);
-    c[5] = keep * p[5] + r2 * LBM_EQ(upv);
-    c[6] = keep * p[6] + r2 * LBM_EQ(-umv);
-    c[7] = keep * p[7] + r2 * LBM_EQ(-upv);
-    c[8] = keep * p[8] + r2 * LBM_EQ(umv);
-#undef LBM_EQ
-    const real e2 = (c[1] + c[5]) + c[8];
-    const real w_2 = (c[3] + c[6]) + c[7];
-    const real n2 = (c[2] + c[5]) + c[6];
-    const real s2 = (c[4] + c[7]) + c[8];
-    const real rho2 = ((c[0] + c[2]) + (c[4] + e2)) + w_2;
-    const real inv2 = fast_rcp(rho2, 1);
-    const real vx = (e2 - w_2) * inv2;
-    const real vy = (n2 - s2) * inv2;
-    speed = fast_sqrt(vx * vx + vy * vy);
+    const FastConsts<real> k(omega);
+    speed = speed_of(collide_fast<real>(p, k, c));
   }
-  // obstacle: bounce-back of the pulled values (d2q9-bgk.c:971-981), no average
-  o[0] = obstacle ? p[0] : c[0];
-  o[1] = obstacle ? p[3] : c[1];
-  o[2] = obstacle ? p[4] : c[2];
-  o[3] = obstacle ? p[1] : c[3];
-  o[4] = obstacle ? p[2] : c[4];
-  o[5] = obstacle ? p[7] : c[5];
-  o[6] = obstacle ? p[8] : c[6];
-  o[7] = obstacle ? p[5] : c[7];
-  o[8] = obstacle ? p[6] : c[8];
-  return obstacle ? (real)0 : speed;
+  if (obstacle) {
+    cell_rebound<real>(p, o);
+    return (real)0;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) o[k] = c[k];
+  return speed;
+}
+
+// Four neighbouring cells of one thread (the unit of the vectorised kernels): in[j] pulled
+// values of cell j, bit j of `obits` set for an obstacle (or padding) cell.  Returns the
+// quad's contribution to the step's fixed-point |u| sum; `bad` is set when a speed is NaN
+// or beyond LBM_SPEED_LIMIT.  Default fp32 build: the cells go through the packed lanes as
+// the pairs (0,1) and (2,3), the rare obstacle cells are patched afterwards, and the four
+// speeds are added as floats -- (s0 + s1) + (s2 + s3), a fixed order on a fixed, aligned set
+// of cells, so the sum does not depend on the decomposition -- and converted once.
+template <typename real, bool STRICT> struct QuadConsts {
+  real omega;
+  __device__ __forceinline__ explicit QuadConsts(real om) : omega(om) {}
+};
+template <> struct QuadConsts<float, false> {
+#if LBM_PACKED
+  FastConsts<float2> k;
+#else
+  FastConsts<float> k;
+#endif
+  __device__ __forceinline__ explicit QuadConsts(float om) : k(om) {}
+};
+template <> struct QuadConsts<double, false> {
+  FastConsts<double> k;
+  __device__ __forceinline__ explicit QuadConsts(double om) : k(om) {}
+};
+
+template <typename real>
+__device__ __forceinline__ unsigned long long quad_sum_fixed(real s0, real s1, real s2, real s3, bool& bad) {
+  typedef Ops<real, true> M;
+  const real s = M::add(M::add(s0, s1), M::add(s2, s3));
+  bad = !(s < (real)LBM_SPEED_LIMIT);
+  return to_fixed(s);
+}
+
+template <typename real, bool STRICT>
+__device__ __forceinline__ unsigned long long quad_update(const real (&in)[4][9], const uint32_t obits,
+                                                          const QuadConsts<real, STRICT>& qc, real (&out)[4][9],
+                                                          bool& bad) {
+  if constexpr (STRICT) {
+    unsigned long long q = 0ULL;
+    bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const real s = cell_update<real, true>(in[j], (obits >> j) & 1u, qc.omega, out[j]);
+      q += to_fixed(s);
+      bad |= !(s < (real)LBM_SPEED_LIMIT);
+    }
+    return q;
+  } else {
+    real s[4];
+    if constexpr (sizeof(real) == 4 && LBM_PACKED) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        float2 p[9], c[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) p[k] = make_float2(in[2 * h][k], in[2 * h + 1][k]);
+        const float2 usq = collide_fast<float2>(p, qc.k, c);
+#pragma unroll
+        for (int k = 0; k < 9; k++) { out[2 * h][k] = c[k].x; out[2 * h + 1][k] = c[k].y; }
+        s[2 * h] = speed_of(usq.x);
+        s[2 * h + 1] = speed_of(usq.y);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) s[j] = speed_of(collide_fast<real>(in[j], qc.k, out[j]));
+    }
+    if (obits != 0u) {            // rare: walls, the 1 % random obstacles of the synthetic channel
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if ((obits >> j) & 1u) { cell_rebound<real>(in[j], out[j]); s[j] = (real)0; }
+    }
+    return quad_sum_fixed<real>(s[0], s[1], s[2], s[3], bad);
+  }
 }
 
 // accelerate_flow on one cell's speeds (d2q9-bgk.c:246-258); a[] = {f1,f3,f5,f6,f7,f8}.
@@ -259,18 +407,22 @@ struct StepArgs {
   real* side_dst;              // same, written for the next step
   const uint32_t* mask;        // rows x mask_pitch words
   unsigned long long* av;      // this step's |u| sums: LBM_AV_SLOTS lines of {low halves, high halves, pad}
-  // halo rows: 3 x pitch each, see "window" above
-  const real* halo_s;          // own window, src parity: speeds {2,5,6} of the row below row 0
-  const real* halo_n;          // own window, src parity: speeds {4,7,8} of the row above row rows-1
-  real* push_up;               // neighbour above's window, dst parity, "from below": {2,5,6}
-  real* push_dn;               // neighbour below's window, dst parity, "from above": {4,7,8}
-  // cross-slab ordering (only when MULTI)
-  volatile unsigned long long* flag_from_below;  // local: steps completed by neighbour below
+  // ghost rows, see "window" above: plane k of depth d at (d * 9 + k) * pitch
+  const real* ghost_s;         // own window, src parity, "from below" (row -1, row -2)
+  const real* ghost_n;         // own window, src parity, "from above" (row rows, row rows+1)
+  real* push_up;               // neighbour above's window, dst parity, "from below"
+  real* push_dn;               // neighbour below's window, dst parity, "from above"
+  // cross-slab ordering (only when MULTI): counters of completed PASSES (kernel launches)
+  volatile unsigned long long* flag_from_below;  // local: passes completed by neighbour below
   volatile unsigned long long* flag_from_above;
   unsigned long long* up_flag;                   // neighbour above's flag_from_below
   unsigned long long* dn_flag;                   // neighbour below's flag_from_above
   unsigned long long* boundary_done;             // local counter of finished boundary blocks
-  unsigned long long step;                       // global index of this step (0-based)
+  unsigned long long* abort_word;                // local: non-zero = give up (set by a neighbour or a time-out)
+  unsigned long long* up_abort;                  // the neighbours' abort words
+  unsigned long long* dn_abort;
+  unsigned long long pass;                       // index of this pass (0-based, since creation)
+  unsigned long long timeout_ns;                 // longest wait for a neighbour
   long long plane_stride;      // rows * pitch
   int nx;
   int rows;                    // local rows
@@ -278,9 +430,17 @@ struct StepArgs {
   int mask_pitch;              // words per mask row
   int accel_row;               // local row holding global row ny-2, or LBM_NO_ROW
   int tiles_x, tiles_y;
+  int edge_tiles;              // tile rows at each end of the slab that touch ghost rows (1; 2 with deep pushes)
+  int deep;                    // also push what the two-step kernel reads: planes 0,1,3 of the edge rows and the second rows
   real omega;
   real aw1, aw2;               // density*accel/9, density*accel/36 (d2q9-bgk.c:230-231)
 };
+
+// offset (in elements) of a section of the ghost rows inside the window
+__host__ __device__ inline size_t ghost_offset(int pitch, int parity, int dir) {
+  return (size_t)((parity * 2 + dir) * 18) * (size_t)pitch;
+}
+#define LBM_GHOST_PLANE_ROWS 72          /* 2 parities x 2 directions x 2 depths x 9 planes */
 
 #define LBM_NO_ROW (-1000)
 
@@ -340,12 +500,14 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Exact sum of the per-thread fixed-point |u| (unit 2^-52).  The sum of a warp (shuffle
-// tree) or of a block is added to the step's accumulators as two fire-and-forget atomics
-// (RED): the low and the high 32-bit half go to two 64-bit words, so that
-// total = (sum of high halves << 32) + sum of low halves with no carry to propagate and no
-// return value to wait for.  LBM_AV_SLOTS such pairs per step, each in its own 128-byte
-// line: one L2 line takes only about 0.47 G atomics/s (measured).
+// Exact sum of the per-thread fixed-point |u| (unit 2^-52).  A per-thread partial sum q is
+// below 2^63 (LBM_SPEED_LIMIT).  It is cut into three pieces of 26 + 26 + 11 bits, each piece
+// is added over the warp with ONE redux.sync (the 32-lane sums fit 32 bits), and lane 0 folds
+// them into a pair {lo, hi} with value = hi * 2^32 + lo.  Pairs are added to the step's
+// accumulators with two fire-and-forget atomics (RED) on two 64-bit words: no carry to
+// propagate, no return value to wait for, no overflow whatever the block or grid size.
+// LBM_AV_SLOTS such pairs per step, each in its own 128-byte line: one L2 line takes only
+// about 0.47 G atomics/s (measured).
 //   block_accumulate  one pair of atomics per block (shared memory + __syncthreads): the
 //                     per-step kernels, where a 16384^2 step has 2.1 M warps -- one pair
 //                     per WARP was measured 8 % slower there (L2 atomic traffic);
@@ -354,10 +516,22 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 #define LBM_AV_SLOTS 8
 #define LBM_AV_STRIDE 16                 /* words between slots: one 128-byte line each */
 
-__device__ __forceinline__ void av_add(unsigned long long q, unsigned long long* av_step, const unsigned slot) {
+struct AvPair { unsigned long long lo, hi; };
+
+__device__ __forceinline__ AvPair warp_reduce_fixed(const unsigned long long q) {
+  const unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)(q & 0x3ffffffULL));
+  const unsigned b = __reduce_add_sync(0xffffffffu, (unsigned)((q >> 26) & 0x3ffffffULL));
+  const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)(q >> 52));
+  AvPair r;
+  r.lo = (unsigned long long)a + ((unsigned long long)b << 26);
+  r.hi = (unsigned long long)c << 20;
+  return r;
+}
+
+__device__ __forceinline__ void av_add(const AvPair v, unsigned long long* av_step, const unsigned slot) {
   unsigned long long* p = av_step + LBM_AV_STRIDE * (slot & (LBM_AV_SLOTS - 1));
-  atomicAdd(p, q & 0xffffffffULL);
-  atomicAdd(p + 1, q >> 32);
+  if (v.lo) atomicAdd(p, v.lo);
+  if (v.hi) atomicAdd(p + 1, v.hi);
 }
 
 __device__ __forceinline__ void warp_accumulate(unsigned long long q, unsigned long long* av_step) {
@@ -365,10 +539,9 @@ __device__ __forceinline__ void warp_accumulate(unsigned long long q, unsigned l
   if (q == 0xffffffffffffffffULL) *av_step = q;   // keeps q alive, never true
   return;
 #endif
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
+  const AvPair v = warp_reduce_fixed(q);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if ((tid & 31) == 0 && q != 0ULL) av_add(q, av_step, blockIdx.x + (tid >> 5));
+  if ((tid & 31) == 0) av_add(v, av_step, blockIdx.x + (tid >> 5));
 }
 
 __device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned long long* av_step) {
@@ -376,18 +549,16 @@ __device__ __forceinline__ void block_accumulate(unsigned long long q, unsigned 
   if (q == 0xffffffffffffffffULL) *av_step = q;   // keeps q alive, never true
   return;
 #endif
-  __shared__ unsigned long long warp_sums[32];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
+  __shared__ AvPair warp_sums[32];
+  const AvPair v = warp_reduce_fixed(q);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
-  if ((tid & 31) == 0) warp_sums[tid >> 5] = q;
+  if ((tid & 31) == 0) warp_sums[tid >> 5] = v;
   __syncthreads();
-  if (tid < 32) {
-    unsigned long long v = (tid < nwarps) ? warp_sums[tid] : 0ULL;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (tid == 0 && v != 0ULL) av_add(v, av_step, blockIdx.x);
+  if (tid == 0) {
+    AvPair t = warp_sums[0];
+    for (int i = 1; i < nwarps; i++) { t.lo += warp_sums[i].lo; t.hi += warp_sums[i].hi; }
+    av_add(t, av_step, blockIdx.x);
   }
 }
 
@@ -411,24 +582,57 @@ __global__ void lbm_compact_av(const unsigned long long* __restrict__ av, unsign
   out[2 * t + 1] = hi | mark;
 }
 
-// Block -> tile mapping.  The row tiles that touch the slab's first and last row are
-// given the lowest block indices so that they are dispatched first: their halo pushes
-// leave early and the neighbours' next step never waits for them.
-__device__ __forceinline__ void tile_of_block(const int tiles_x, const int tiles_y, int& tx, int& ty) {
+// Block -> tile mapping.  The `edge` tile rows at each end of the slab (those that read
+// ghost rows or push into the neighbours) get the lowest block indices so that they are
+// dispatched first: their pushes leave early and the neighbours' next pass never waits.
+__device__ __forceinline__ void tile_of_block(const int tiles_x, const int tiles_y, const int edge, int& tx, int& ty) {
   const unsigned b = blockIdx.x;
-  const unsigned slot = b / (unsigned)tiles_x;
-  tx = (int)(b - slot * (unsigned)tiles_x);
-  if (slot == 0) ty = 0;
-  else if (slot == 1) ty = tiles_y - 1;
-  else ty = (int)slot - 1;
+  const int slot = (int)(b / (unsigned)tiles_x);
+  tx = (int)(b - (unsigned)slot * (unsigned)tiles_x);
+  if (tiles_y < 2 * edge) ty = slot;                       // tiny slab: every tile row is an edge
+  else if (slot < edge) ty = slot;
+  else if (slot < 2 * edge) ty = tiles_y - 1 - (slot - edge);
+  else ty = slot - edge;
+}
+__device__ __forceinline__ bool is_edge_tile(const int ty, const int tiles_y, const int edge) {
+  return (ty < edge) || (ty >= tiles_y - edge);
+}
+__host__ __device__ inline unsigned long long edge_tile_count(int tiles_x, int tiles_y, int edge) {
+  return (unsigned long long)tiles_x * (unsigned long long)(tiles_y < 2 * edge ? tiles_y : 2 * edge);
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// error codes left in the sync block for the host (kSyncError)
+#define LBM_SYNC_TIMEOUT 1ULL
+#define LBM_SYNC_ABORTED 2ULL
+
+// Wait until both neighbours have completed `pass` passes.  The wait is bounded: when a
+// neighbour does not arrive within timeout_ns (its process died, or it was asked for a
+// different number of steps), or when the abort word is set, the block records the reason,
+// raises the abort word here AND in both neighbours (so that the whole ring drains instead
+// of every slab timing out in turn), and carries on -- the results of this run are void and
+// lbm_gpu_run reports the failure (the reference's convention is die(), d2q9-bgk.c:3001).
 template <typename real, bool MULTI>
 __device__ __forceinline__ void boundary_wait(const StepArgs<real>& a, const bool is_boundary) {
   if (MULTI && is_boundary) {
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-      while (ld_acquire_sys(a.flag_from_below) < a.step) { }
-      while (ld_acquire_sys(a.flag_from_above) < a.step) { }
+      const unsigned long long t0 = global_timer_ns();
+      unsigned long long why = 0ULL;
+      while (ld_acquire_sys(a.flag_from_below) < a.pass || ld_acquire_sys(a.flag_from_above) < a.pass) {
+        if (ld_acquire_sys(a.abort_word) != 0ULL) { why = LBM_SYNC_ABORTED; break; }
+        if (global_timer_ns() - t0 > a.timeout_ns) { why = LBM_SYNC_TIMEOUT; break; }
+      }
+      if (why != 0ULL) {
+        atomicCAS(a.abort_word + 1, 0ULL, (why << 56) | (a.pass & 0xffffffffffffffULL));   // first reason wins
+        st_release_sys(a.abort_word, 1ULL);
+        st_release_sys(a.up_abort, 1ULL);
+        st_release_sys(a.dn_abort, 1ULL);
+      }
     }
     __syncthreads();
   }
@@ -437,18 +641,26 @@ __device__ __forceinline__ void boundary_wait(const StepArgs<real>& a, const boo
 template <typename real, bool MULTI>
 __device__ __forceinline__ void boundary_signal(const StepArgs<real>& a, const bool is_boundary) {
   if (MULTI && is_boundary) {
-    __threadfence_system();            // this thread's halo pushes are visible system-wide
+    __threadfence_system();            // this thread's ghost-row pushes are visible system-wide
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-      const unsigned long long nb = (unsigned long long)a.tiles_x * (a.tiles_y > 1 ? 2ULL : 1ULL);
+      const unsigned long long nb = edge_tile_count(a.tiles_x, a.tiles_y, a.edge_tiles);
       const unsigned long long old = atomicAdd(a.boundary_done, 1ULL);
-      if (old + 1ULL == nb * (a.step + 1ULL)) {
+      if (old + 1ULL == nb * (a.pass + 1ULL)) {
         __threadfence_system();
-        st_release_sys(a.up_flag, a.step + 1ULL);
-        st_release_sys(a.dn_flag, a.step + 1ULL);
+        st_release_sys(a.up_flag, a.pass + 1ULL);
+        st_release_sys(a.dn_flag, a.pass + 1ULL);
       }
     }
   }
+}
+
+// End of a run: one thread waits (bounded, like boundary_wait) until both neighbours have
+// completed `pass` passes too.  After it nothing of this run is still in flight towards this
+// slab's window, so the host may destroy, upload or re-create without a barrier of its own.
+template <typename real>
+__global__ void lbm_wait_neighbours(const StepArgs<real> a) {
+  boundary_wait<real, true>(a, true);
 }
 
 // ------------------------------------------------------------------------------------
@@ -459,35 +671,43 @@ __device__ __forceinline__ void boundary_signal(const StepArgs<real>& a, const b
 // blockDim = (BX, BY), BX a multiple of 32 so that a warp never spans two rows.
 // ------------------------------------------------------------------------------------
 template <typename real, bool STRICT, bool CG>
-__device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a, const int tx, const int ty) {
+__device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a, const QuadConsts<real, STRICT>& qc,
+                                                        const int tx, const int ty) {
   const int x0 = (tx * (int)blockDim.x + (int)threadIdx.x) * 4;
   const int r = ty * (int)blockDim.y + (int)threadIdx.y;        // local row
   const bool active = (x0 < a.nx) && (r < a.rows);
   const int lane = threadIdx.x & 31;
-  unsigned long long q = 0ULL;
 
   // clamp so that inactive threads still form valid addresses (they take part in the
   // shuffles but never store)
   const int xc = active ? x0 : 0;
   const int rc = active ? r : 0;
   const long long PS = a.plane_stride;
-  const long long oC = (long long)rc * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
+  const long long oC = (long long)rc * a.pitch;
 
   // Row sources.  South/north neighbours of the slab's first/last row live in the halo
   // window; planes 1,3 of the centre row / 5,6 of the south row / 7,8 of the north row
   // come from the accelerated side row when that row is global row ny-2 (the window
-  // already holds accelerated values).  All of this is warp-uniform.
+  // already holds accelerated values).  All of this is warp-uniform, and all but five
+  // rows of a slab take the first branch.
   const bool first = (rc == 0), last = (rc == a.rows - 1);
   const bool cA = (rc == a.accel_row), sA = (rc - 1 == a.accel_row), nA = (rc + 1 == a.accel_row);
-  const real* p0 = a.src + oC;
-  const real* p1 = cA ? a.side_src + 0 * a.pitch : a.src + 1 * PS + oC;
-  const real* p3 = cA ? a.side_src + 1 * a.pitch : a.src + 3 * PS + oC;
-  const real* p2 = first ? a.halo_s + 0 * a.pitch : a.src + 2 * PS + oS;
-  const real* p5 = first ? a.halo_s + 1 * a.pitch : (sA ? a.side_src + 2 * a.pitch : a.src + 5 * PS + oS);
-  const real* p6 = first ? a.halo_s + 2 * a.pitch : (sA ? a.side_src + 3 * a.pitch : a.src + 6 * PS + oS);
-  const real* p4 = last ? a.halo_n + 0 * a.pitch : a.src + 4 * PS + oN;
-  const real* p7 = last ? a.halo_n + 1 * a.pitch : (nA ? a.side_src + 4 * a.pitch : a.src + 7 * PS + oN);
-  const real* p8 = last ? a.halo_n + 2 * a.pitch : (nA ? a.side_src + 5 * a.pitch : a.src + 8 * PS + oN);
+  const real *p0, *p1, *p2, *p3, *p4, *p5, *p6, *p7, *p8;
+  {
+    const real* c = a.src + oC;
+    const real* sr = c - a.pitch;
+    const real* nr = c + a.pitch;
+    p0 = c;          p1 = c + PS;      p3 = c + 3 * PS;
+    p2 = sr + 2 * PS; p5 = sr + 5 * PS; p6 = sr + 6 * PS;
+    p4 = nr + 4 * PS; p7 = nr + 7 * PS; p8 = nr + 8 * PS;
+  }
+  if (first | last | cA | sA | nA) {
+    if (cA) { p1 = a.side_src + 0 * a.pitch; p3 = a.side_src + 1 * a.pitch; }
+    if (sA) { p5 = a.side_src + 2 * a.pitch; p6 = a.side_src + 3 * a.pitch; }
+    if (nA) { p7 = a.side_src + 4 * a.pitch; p8 = a.side_src + 5 * a.pitch; }
+    if (first) { p2 = a.ghost_s + 2 * a.pitch; p5 = a.ghost_s + 5 * a.pitch; p6 = a.ghost_s + 6 * a.pitch; }
+    if (last) { p4 = a.ghost_n + 4 * a.pitch; p7 = a.ghost_n + 7 * a.pitch; p8 = a.ghost_n + 8 * a.pitch; }
+  }
 
   // edge elements first (scalar, predicated), then the nine aligned vectors
   const bool need_w = (lane == 0) || (xc == 0);
@@ -509,80 +729,71 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
        l8 = __shfl_up_sync(0xffffffffu, v8.w, 1);
   real r3 = __shfl_down_sync(0xffffffffu, v3.x, 1), r6 = __shfl_down_sync(0xffffffffu, v6.x, 1),
        r7 = __shfl_down_sync(0xffffffffu, v7.x, 1);
-  if (need_w) { l1 = w1e; l5 = w5e; l8 = w8e; }
-  if (need_e) { r3 = e3e; r6 = e6e; r7 = e7e; }
-
-  real in[4][9], out[4][9];
-  in[0][0] = v0.x; in[1][0] = v0.y; in[2][0] = v0.z; in[3][0] = v0.w;
-  in[0][1] = l1;   in[1][1] = v1.x; in[2][1] = v1.y; in[3][1] = v1.z;
-  in[0][2] = v2.x; in[1][2] = v2.y; in[2][2] = v2.z; in[3][2] = v2.w;
-  in[0][3] = v3.y; in[1][3] = v3.z; in[2][3] = v3.w; in[3][3] = r3;
-  in[0][4] = v4.x; in[1][4] = v4.y; in[2][4] = v4.z; in[3][4] = v4.w;
-  in[0][5] = l5;   in[1][5] = v5.x; in[2][5] = v5.y; in[3][5] = v5.z;
-  in[0][6] = v6.y; in[1][6] = v6.z; in[2][6] = v6.w; in[3][6] = r6;
-  in[0][7] = v7.y; in[1][7] = v7.z; in[2][7] = v7.w; in[3][7] = r7;
-  in[0][8] = l8;   in[1][8] = v8.x; in[2][8] = v8.y; in[3][8] = v8.z;
+  l1 = need_w ? w1e : l1; l5 = need_w ? w5e : l5; l8 = need_w ? w8e : l8;
+  r3 = need_e ? e3e : r3; r6 = need_e ? e6e : r6; r7 = need_e ? e7e : r7;
 
   // Widths that are not a multiple of 4: the row's last thread holds 1-3 valid cells, the
   // rest of its vector is row padding (loaded and stored, never used).  The east neighbour
   // of the last valid cell is column 0 -- the wrap element r3/r6/r7 already holds -- and the
   // padding cells are treated as obstacles so that they add nothing to the average.
-  uint32_t obits = mbits;
   const int nvalid = a.nx - xc;
-  if (nvalid < 4) {
-    if (nvalid == 1) { in[0][3] = r3; in[0][6] = r6; in[0][7] = r7; }
-    else if (nvalid == 2) { in[1][3] = r3; in[1][6] = r6; in[1][7] = r7; }
-    else { in[2][3] = r3; in[2][6] = r6; in[2][7] = r7; }
-    obits |= (0xFu << nvalid) & 0xFu;
-  }
+  const bool n1 = (nvalid == 1), n2 = (nvalid == 2), n3 = (nvalid == 3);
+  const uint32_t obits = (nvalid < 4) ? (mbits | ((0xFu << nvalid) & 0xFu)) : mbits;
 
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const real s = cell_update<real, STRICT>(in[j], (obits >> j) & 1u, a.omega, out[j]);
-    q += to_fixed(s);
-    if (active && !(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av + 1, LBM_NONFINITE_MARK);   // NaN / blow-up
-  }
+  real in[4][9], out[4][9];
+  in[0][0] = v0.x; in[1][0] = v0.y; in[2][0] = v0.z; in[3][0] = v0.w;
+  in[0][1] = l1;   in[1][1] = v1.x; in[2][1] = v1.y; in[3][1] = v1.z;
+  in[0][2] = v2.x; in[1][2] = v2.y; in[2][2] = v2.z; in[3][2] = v2.w;
+  in[0][3] = n1 ? r3 : v3.y; in[1][3] = n2 ? r3 : v3.z; in[2][3] = n3 ? r3 : v3.w; in[3][3] = r3;
+  in[0][4] = v4.x; in[1][4] = v4.y; in[2][4] = v4.z; in[3][4] = v4.w;
+  in[0][5] = l5;   in[1][5] = v5.x; in[2][5] = v5.y; in[3][5] = v5.z;
+  in[0][6] = n1 ? r6 : v6.y; in[1][6] = n2 ? r6 : v6.z; in[2][6] = n3 ? r6 : v6.w; in[3][6] = r6;
+  in[0][7] = n1 ? r7 : v7.y; in[1][7] = n2 ? r7 : v7.z; in[2][7] = n3 ? r7 : v7.w; in[3][7] = r7;
+  in[0][8] = l8;   in[1][8] = v8.x; in[2][8] = v8.y; in[3][8] = v8.z;
 
-  if (active) {
-    real* d = a.dst + oC + xc;
+  bool bad;
+  unsigned long long q = quad_update<real, STRICT>(in, obits, qc, out, bad);
+  if (!active) return 0ULL;
+  if (bad) atomicOr(a.av + 1, LBM_NONFINITE_MARK);            // NaN / blow-up
+
+  real* d = a.dst + oC + xc;
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
-      Vec4<real> v; v.x = out[0][k]; v.y = out[1][k]; v.z = out[2][k]; v.w = out[3][k];
-      st4(d + k * PS, v);
-    }
-    if (first | last | cA) {          // warp-uniform: a warp never spans two rows
-      if (cA) {
-        // next step's accelerate_flow on the row just produced (d2q9-bgk.c:229-260)
+  for (int k = 0; k < 9; k++) {
+    Vec4<real> v; v.x = out[0][k]; v.y = out[1][k]; v.z = out[2][k]; v.w = out[3][k];
+    st4(d + k * PS, v);
+  }
+  const bool second = a.deep && (rc == 1), before_last = a.deep && (rc == a.rows - 2);
+  if (first | last | cA | second | before_last) {          // warp-uniform: a warp never spans two rows
+    if (cA) {
+      // next step's accelerate_flow on the row just produced (d2q9-bgk.c:229-260)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          cell_accelerate<real, STRICT>(out[j][1], out[j][3], out[j][5], out[j][6], out[j][7], out[j][8],
-                                        (mbits >> j) & 1u, a.aw1, a.aw2);
-        const int ks[6] = {1, 3, 5, 6, 7, 8};
+      for (int j = 0; j < 4; j++)
+        cell_accelerate<real, STRICT>(out[j][1], out[j][3], out[j][5], out[j][6], out[j][7], out[j][8],
+                                      (mbits >> j) & 1u, a.aw1, a.aw2);
+      const int ks[6] = {1, 3, 5, 6, 7, 8};
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
-          st4(a.side_dst + (long long)i * a.pitch + xc, v);
-        }
-      }
-      if (first) {                    // speeds 4,7,8 are pulled by the row below
-        const int ks[3] = {4, 7, 8};
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
-          st4(a.push_dn + (long long)i * a.pitch + xc, v);
-        }
-      }
-      if (last) {                     // speeds 2,5,6 are pulled by the row above
-        const int ks[3] = {2, 5, 6};
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
-          st4(a.push_up + (long long)i * a.pitch + xc, v);
-        }
+      for (int i = 0; i < 6; i++) {
+        Vec4<real> v; v.x = out[0][ks[i]]; v.y = out[1][ks[i]]; v.z = out[2][ks[i]]; v.w = out[3][ks[i]];
+        st4(a.side_dst + (long long)i * a.pitch + xc, v);
       }
     }
-  } else {
-    q = 0ULL;
+    // ghost rows of the neighbours: the row below pulls speeds 4,7,8 of this slab's first
+    // row, the row above 2,5,6 of its last row; the two-step kernel also wants 0,1,3 of those
+    // rows (depth 0) and 4,7,8 / 2,5,6 of the second / second-to-last row (depth 1)
+#define LBM_PUSH(dst, depth, k)                                                                          \
+  { Vec4<real> v; v.x = out[0][k]; v.y = out[1][k]; v.z = out[2][k]; v.w = out[3][k];                      \
+    st4((dst) + (long long)((depth) * 9 + (k)) * a.pitch + xc, v); }
+    if (first) {
+      LBM_PUSH(a.push_dn, 0, 4) LBM_PUSH(a.push_dn, 0, 7) LBM_PUSH(a.push_dn, 0, 8)
+      if (a.deep) { LBM_PUSH(a.push_dn, 0, 0) LBM_PUSH(a.push_dn, 0, 1) LBM_PUSH(a.push_dn, 0, 3) }
+    }
+    if (last) {
+      LBM_PUSH(a.push_up, 0, 2) LBM_PUSH(a.push_up, 0, 5) LBM_PUSH(a.push_up, 0, 6)
+      if (a.deep) { LBM_PUSH(a.push_up, 0, 0) LBM_PUSH(a.push_up, 0, 1) LBM_PUSH(a.push_up, 0, 3) }
+    }
+    if (second) { LBM_PUSH(a.push_dn, 1, 4) LBM_PUSH(a.push_dn, 1, 7) LBM_PUSH(a.push_dn, 1, 8) }
+    if (before_last) { LBM_PUSH(a.push_up, 1, 2) LBM_PUSH(a.push_up, 1, 5) LBM_PUSH(a.push_up, 1, 6) }
+#undef LBM_PUSH
   }
   return q;
 }
@@ -591,15 +802,16 @@ template <typename real, bool STRICT, bool MULTI>
 __global__ void __launch_bounds__(LBM_BLOCK_THREADS, (sizeof(real) == 4 ? LBM_MIN_BLOCKS : 1))
 lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
   int tx, ty;
-  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
+  tile_of_block(a.tiles_x, a.tiles_y, a.edge_tiles, tx, ty);
   // Programmatic dependent launch: when the host launches the steps with
   // cudaLaunchAttributeProgrammaticStreamSerialization this grid may be scheduled while
   // the previous step drains; everything the previous step wrote is visible after this
   // call.  A no-op for an ordinary launch.
   cudaGridDependencySynchronize();
-  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  const bool is_boundary = is_edge_tile(ty, a.tiles_y, a.edge_tiles);
   boundary_wait<real, MULTI>(a, is_boundary);
-  const unsigned long long q = vec4_tile<real, STRICT, false>(a, tx, ty);
+  const QuadConsts<real, STRICT> qc(a.omega);
+  const unsigned long long q = vec4_tile<real, STRICT, false>(a, qc, tx, ty);
   block_accumulate(q, a.av);
   boundary_signal<real, MULTI>(a, is_boundary);
 }
@@ -633,16 +845,17 @@ lbm_step_tma(const __grid_constant__ StepArgs<float> a, const __grid_constant__ 
                                                       // (rows 128 B apart: TMA destinations are 128-byte aligned)
   __shared__ alignas(8) unsigned long long mbar;
   int tx, ty;
-  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
-  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  tile_of_block(a.tiles_x, a.tiles_y, a.edge_tiles, tx, ty);
+  const bool is_boundary = is_edge_tile(ty, a.tiles_y, a.edge_tiles);
   boundary_wait<float, MULTI>(a, is_boundary);
 
   const int r = ty;                                   // blockDim = (LBM_BLOCK_THREADS, 1): one row per tile
   const bool special = (r == 0) || (r == a.rows - 1) || (r == a.accel_row) || (r - 1 == a.accel_row) ||
                        (r + 1 == a.accel_row);
   unsigned long long q = 0ULL;
+  const QuadConsts<float, STRICT> qc(a.omega);
   if (special) {
-    q = vec4_tile<float, STRICT, false>(a, tx, ty);
+    q = vec4_tile<float, STRICT, false>(a, qc, tx, ty);
   } else {
     const int tid = threadIdx.x;
     const int xt = tx * LBM_TMA_TILE;                 // first column of the tile
@@ -719,12 +932,9 @@ lbm_step_tma(const __grid_constant__ StepArgs<float> a, const __grid_constant__ 
       else { in[3][3] = e3e; in[3][6] = e6e; in[3][7] = e7e; }
       if (nvalid < 4) obits |= (0xFu << nvalid) & 0xFu;
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const float s = cell_update<float, STRICT>(in[j], (obits >> j) & 1u, a.omega, out[j]);
-      q += to_fixed(s);
-      if (active && !(s < (float)LBM_SPEED_LIMIT)) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
-    }
+    bool bad;
+    q = quad_update<float, STRICT>(in, obits, qc, out, bad);
+    if (active && bad) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
     if (active) {
       float* d = a.dst + oC + x0;
 #pragma unroll
@@ -750,7 +960,7 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
   const int x = tx * (int)blockDim.x + (int)threadIdx.x;
   const int r = ty * (int)blockDim.y + (int)threadIdx.y;
   const bool active = (x < a.nx) && (r < a.rows);
-  unsigned long long q = 0ULL;
+  real s = (real)0;
   if (active) {
     const long long PS = a.plane_stride;
     const long long oC = (long long)r * a.pitch, oS = oC - a.pitch, oN = oC + a.pitch;
@@ -762,16 +972,14 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
     p[0] = LD(a.src + oC + x);
     p[1] = cA ? LD(a.side_src + 0 * a.pitch + xw) : LD(a.src + 1 * PS + oC + xw);
     p[3] = cA ? LD(a.side_src + 1 * a.pitch + xe) : LD(a.src + 3 * PS + oC + xe);
-    p[2] = first ? LD(a.halo_s + 0 * a.pitch + x) : LD(a.src + 2 * PS + oS + x);
-    p[5] = first ? LD(a.halo_s + 1 * a.pitch + xw) : (sA ? LD(a.side_src + 2 * a.pitch + xw) : LD(a.src + 5 * PS + oS + xw));
-    p[6] = first ? LD(a.halo_s + 2 * a.pitch + xe) : (sA ? LD(a.side_src + 3 * a.pitch + xe) : LD(a.src + 6 * PS + oS + xe));
-    p[4] = last ? LD(a.halo_n + 0 * a.pitch + x) : LD(a.src + 4 * PS + oN + x);
-    p[7] = last ? LD(a.halo_n + 1 * a.pitch + xe) : (nA ? LD(a.side_src + 4 * a.pitch + xe) : LD(a.src + 7 * PS + oN + xe));
-    p[8] = last ? LD(a.halo_n + 2 * a.pitch + xw) : (nA ? LD(a.side_src + 5 * a.pitch + xw) : LD(a.src + 8 * PS + oN + xw));
+    p[2] = first ? LD(a.ghost_s + 2 * a.pitch + x) : LD(a.src + 2 * PS + oS + x);
+    p[5] = first ? LD(a.ghost_s + 5 * a.pitch + xw) : (sA ? LD(a.side_src + 2 * a.pitch + xw) : LD(a.src + 5 * PS + oS + xw));
+    p[6] = first ? LD(a.ghost_s + 6 * a.pitch + xe) : (sA ? LD(a.side_src + 3 * a.pitch + xe) : LD(a.src + 6 * PS + oS + xe));
+    p[4] = last ? LD(a.ghost_n + 4 * a.pitch + x) : LD(a.src + 4 * PS + oN + x);
+    p[7] = last ? LD(a.ghost_n + 7 * a.pitch + xe) : (nA ? LD(a.side_src + 4 * a.pitch + xe) : LD(a.src + 7 * PS + oN + xe));
+    p[8] = last ? LD(a.ghost_n + 8 * a.pitch + xw) : (nA ? LD(a.side_src + 5 * a.pitch + xw) : LD(a.src + 8 * PS + oN + xw));
     const bool obst = (a.mask[(long long)r * a.mask_pitch + (x >> 5)] >> (x & 31)) & 1u;
-    const real s = cell_update<real, STRICT>(p, obst, a.omega, o);
-    q = to_fixed(s);
-    if (!(s < (real)LBM_SPEED_LIMIT)) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
+    s = cell_update<real, STRICT>(p, obst, a.omega, o);
 #pragma unroll
     for (int k = 0; k < 9; k++) a.dst[k * PS + oC + x] = o[k];
     if (cA) {
@@ -781,17 +989,34 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
       a.side_dst[4 * a.pitch + x] = o[7]; a.side_dst[5 * a.pitch + x] = o[8];
     }
     if (first) {
-      a.push_dn[0 * a.pitch + x] = o[4];
-      a.push_dn[1 * a.pitch + x] = o[7];
-      a.push_dn[2 * a.pitch + x] = o[8];
+      a.push_dn[4 * a.pitch + x] = o[4];
+      a.push_dn[7 * a.pitch + x] = o[7];
+      a.push_dn[8 * a.pitch + x] = o[8];
     }
     if (last) {
-      a.push_up[0 * a.pitch + x] = o[2];
-      a.push_up[1 * a.pitch + x] = o[5];
-      a.push_up[2 * a.pitch + x] = o[6];
+      a.push_up[2 * a.pitch + x] = o[2];
+      a.push_up[5 * a.pitch + x] = o[5];
+      a.push_up[6 * a.pitch + x] = o[6];
     }
   }
 #undef LD
+  // |u| sum: the strict build converts every cell exactly; the default build adds the four
+  // cells of an aligned quad as floats in the order of the vectorised kernels (quad_update),
+  // so that every kernel variant returns the same av_vels bits.
+  unsigned long long q;
+  bool bad;
+  if (STRICT) {
+    q = to_fixed(s);
+    bad = !(s < (real)LBM_SPEED_LIMIT);
+  } else {
+    typedef Ops<real, true> M;
+    real t = M::add(s, __shfl_xor_sync(0xffffffffu, s, 1));
+    t = M::add(t, __shfl_xor_sync(0xffffffffu, t, 2));
+    const bool lead = (threadIdx.x & 3) == 0;
+    q = lead ? to_fixed(t) : 0ULL;
+    bad = lead && !(t < (real)LBM_SPEED_LIMIT);
+  }
+  if (active && bad) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
   return q;
 }
 
@@ -799,8 +1024,8 @@ template <typename real, bool STRICT, bool MULTI>
 __global__ void __launch_bounds__(LBM_BLOCK_THREADS)
 lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
   int tx, ty;
-  tile_of_block(a.tiles_x, a.tiles_y, tx, ty);
-  const bool is_boundary = (ty == 0) || (ty == a.tiles_y - 1);
+  tile_of_block(a.tiles_x, a.tiles_y, a.edge_tiles, tx, ty);
+  const bool is_boundary = is_edge_tile(ty, a.tiles_y, a.edge_tiles);
   boundary_wait<real, MULTI>(a, is_boundary);
   const unsigned long long q = scalar_tile<real, STRICT, false>(a, tx, ty);
   block_accumulate(q, a.av);
@@ -823,7 +1048,7 @@ struct PersistArgs {
   StepArgs<real> s;            // geometry, constants and the step-0 pointers
   real* lattice[2];
   real* side[2];
-  real* window;                // own window: section (parity b, direction d) at ((b*2+d)*3)*pitch
+  real* window;                // own window: ghost rows at ghost_offset(pitch, parity, direction)
   unsigned long long* av;      // n_steps x LBM_AV_SLOTS x LBM_AV_STRIDE words
   unsigned long long* barrier; // zeroed before the launch
   int first_parity;            // buffer index read by the first step
@@ -837,12 +1062,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
   return v;
 }
 
+// All blocks are resident (cooperative launch), so the wait ends unless a block has faulted;
+// the spin is still bounded (about a minute) and ends in a trap, which the host sees as a
+// CUDA error on its next call instead of a kernel that never returns.
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, const unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     __threadfence();
     atomicAdd(counter, 1ULL);
-    while (ld_acquire_gpu(counter) < target) { }
+    unsigned spins = 0;
+    while (ld_acquire_gpu(counter) < target) {
+      if (++spins == 0x10000000u) __trap();
+    }
     __threadfence();
   }
   __syncthreads();
@@ -853,23 +1084,24 @@ __global__ void __launch_bounds__(LBM_BLOCK_THREADS, (sizeof(real) == 4 ? LBM_PE
 lbm_steps_persistent(const __grid_constant__ PersistArgs<real> pa) {
   StepArgs<real> a = pa.s;
   const int pitch = a.pitch;
+  const QuadConsts<real, STRICT> qc(a.omega);
   for (int t = 0; t < pa.n_steps; t++) {
     const int src = (pa.first_parity + t) & 1, dst = src ^ 1;
     a.src = pa.lattice[src];
     a.dst = pa.lattice[dst];
     a.side_src = pa.side[src];
     a.side_dst = pa.side[dst];
-    a.halo_s = pa.window + (size_t)((src * 2 + 0) * 3) * pitch;
-    a.halo_n = pa.window + (size_t)((src * 2 + 1) * 3) * pitch;
-    a.push_up = pa.window + (size_t)((dst * 2 + 0) * 3) * pitch;
-    a.push_dn = pa.window + (size_t)((dst * 2 + 1) * 3) * pitch;
+    a.ghost_s = pa.window + ghost_offset(pitch, src, 0);
+    a.ghost_n = pa.window + ghost_offset(pitch, src, 1);
+    a.push_up = pa.window + ghost_offset(pitch, dst, 0);
+    a.push_dn = pa.window + ghost_offset(pitch, dst, 1);
     a.av = pa.av + (size_t)t * (LBM_AV_STRIDE * LBM_AV_SLOTS);
 #if LBM_K5_EXPERIMENT != 2
     unsigned long long q = 0ULL;
     for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
       const int ty = tile / a.tiles_x;
       const int tx = tile - ty * a.tiles_x;
-      q += (VEC == 4) ? vec4_tile<real, STRICT, true>(a, tx, ty) : scalar_tile<real, STRICT, true>(a, tx, ty);
+      q += (VEC == 4) ? vec4_tile<real, STRICT, true>(a, qc, tx, ty) : scalar_tile<real, STRICT, true>(a, tx, ty);
     }
     warp_accumulate(q, a.av);
 #endif
@@ -894,21 +1126,30 @@ struct PrepareArgs {
   const uint32_t* mask;
   real* push_up;              // neighbour above's window, current parity, "from below"
   real* push_dn;              // neighbour below's window, current parity, "from above"
+  uint32_t* mask_up;          // neighbour above's copy of the mask of ITS row -1 (= this slab's last row)
+  uint32_t* mask_dn;          // neighbour below's copy of the mask of ITS row `rows` (= this slab's first row)
   long long plane_stride;
   int nx, rows, pitch, mask_pitch, accel_row;
+  int deep;                   // also fill what the two-step kernel reads (see "window")
   real aw1, aw2;
 };
 
 template <typename real>
 __global__ void lbm_prepare(const PrepareArgs<real> a) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < a.mask_pitch) {
+    a.mask_dn[x] = a.mask[x];
+    a.mask_up[x] = a.mask[(long long)(a.rows - 1) * a.mask_pitch + x];
+  }
   if (x >= a.nx) return;
   const long long PS = a.plane_stride;
 #pragma unroll 1
-  for (int which = 0; which < 3; which++) {
-    // 0: accelerate row -> side; 1: first row -> push down; 2: last row -> push up
-    const int r = (which == 0) ? a.accel_row : (which == 1 ? 0 : a.rows - 1);
-    if (r < 0) continue;
+  for (int which = 0; which < 5; which++) {
+    // 0: accelerate row -> side; 1: first row -> down, depth 0; 2: last row -> up, depth 0;
+    // 3: second row -> down, depth 1; 4: second-to-last row -> up, depth 1
+    const int r = (which == 0) ? a.accel_row : (which == 1) ? 0 : (which == 2) ? a.rows - 1 : (which == 3) ? 1 : a.rows - 2;
+    if (r < 0 || r >= a.rows) continue;
+    if (which >= 3 && !a.deep) continue;
     const long long o = (long long)r * a.pitch + x;
     real f[9];
 #pragma unroll
@@ -921,14 +1162,18 @@ __global__ void lbm_prepare(const PrepareArgs<real> a) {
       a.side_cur[0 * a.pitch + x] = f[1]; a.side_cur[1 * a.pitch + x] = f[3];
       a.side_cur[2 * a.pitch + x] = f[5]; a.side_cur[3 * a.pitch + x] = f[6];
       a.side_cur[4 * a.pitch + x] = f[7]; a.side_cur[5 * a.pitch + x] = f[8];
-    } else if (which == 1) {
-      a.push_dn[0 * a.pitch + x] = f[4];
-      a.push_dn[1 * a.pitch + x] = f[7];
-      a.push_dn[2 * a.pitch + x] = f[8];
     } else {
-      a.push_up[0 * a.pitch + x] = f[2];
-      a.push_up[1 * a.pitch + x] = f[5];
-      a.push_up[2 * a.pitch + x] = f[6];
+      const bool down = (which == 1 || which == 3);
+      real* dst = (down ? a.push_dn : a.push_up) + (long long)(which >= 3 ? 9 : 0) * a.pitch + x;
+      const int k0 = down ? 4 : 2, k1 = down ? 7 : 5, k2 = down ? 8 : 6;
+      dst[(long long)k0 * a.pitch] = f[k0];
+      dst[(long long)k1 * a.pitch] = f[k1];
+      dst[(long long)k2 * a.pitch] = f[k2];
+      if (which < 3 && a.deep) {
+        dst[0] = f[0];
+        dst[(long long)1 * a.pitch] = f[1];
+        dst[(long long)3 * a.pitch] = f[3];
+      }
     }
   }
 }

@@ -52,6 +52,21 @@ def exchange_descriptors(desc, rank, world, dist=None):
     return parts[below].cpu().numpy(), parts[above].cpu().numpy()
 
 
+def gather_descriptors(desc, world, dist=None):
+    """All-gather the per-rank IPC descriptors -> (world, IPC_DESC_BYTES) uint8, for
+    lbm_gpu_ipc_connect_all (the library finds its neighbours and the whole-grid facts itself)."""
+    desc = np.ascontiguousarray(desc, dtype=np.uint8)
+    if world == 1:
+        return desc.reshape(1, -1)
+    import torch
+    t = torch.from_numpy(desc.copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return np.stack([p.cpu().numpy() for p in parts])
+
+
 def combine_step_sums(local_sums, local_free, dist=None, world=1):
     """Per-step sums of |u| and free-cell counts added over ranks -> av_vels (float64).
 

@@ -76,9 +76,16 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
 #define LBM_GPU_POOL         128u  /* take the lattice from the device's stream-ordered memory pool and
                                       leave it there on destroy: a host that creates many lattices in
                                       one process (sweeps) skips cudaMalloc/cudaFree of ~20 GB each time */
-#define LBM_GPU_SYNC_FLAGS    32u  /* lbm_gpu_create with n_gpus > 1: order the slabs with the
-                                      device-side flag protocol of the one-process-per-GPU form
-                                      instead of CUDA events (every slab on its own GPU) */
+#define LBM_GPU_SYNC_FLAGS    32u  /* lbm_gpu_create with n_gpus > 1: insist on the device-side flag
+                                      protocol between the slabs (the default whenever every slab has a
+                                      GPU of its own; an error if two slabs share one) */
+#define LBM_GPU_KERNEL_TB2   512u  /* force the two-timesteps-per-pass kernel (temporal blocking: each
+                                      distribution crosses HBM once per TWO timesteps).  The default for
+                                      fp32 grids beyond L2 with nx a multiple of 4, nx >= 512 and at least
+                                      8 rows per GPU; an odd step of a run is done by the one-step kernel */
+#define LBM_GPU_SYNC_EVENTS 1024u  /* lbm_gpu_create with n_gpus > 1: order the slabs with CUDA events
+                                      (host-recorded, no device-side waiting) even when every slab has its
+                                      own GPU; always used when slabs share a GPU */
 
 /* Information about a handle (lbm_gpu_get_info). */
 typedef struct {
@@ -125,13 +132,28 @@ int lbm_gpu_create_f64(const lbm_param_f64* params, const double* cells_aos, con
  *   1. lbm_gpu_ipc_export() its descriptor,
  *   2. exchange descriptors with the ranks holding the rows below (row0-1, periodic)
  *      and above (row0+nrows, periodic) by any host-side means,
- *   3. lbm_gpu_ipc_connect() with those two descriptors,
+ *   3. lbm_gpu_ipc_connect() with those two descriptors -- or, better, all-gather the
+ *      descriptors of ALL ranks and call lbm_gpu_ipc_connect_all(): the library then finds
+ *      its two neighbours itself, learns the whole grid's free-cell count (so lbm_gpu_run
+ *      returns true averages without lbm_gpu_set_global_free_cells) and, knowing every
+ *      slab's height, may select the two-timesteps-per-pass kernel, a decision all ranks
+ *      must share (with the two-descriptor form the one-step kernel is kept),
  *   4. pass a host barrier over all ranks, then lbm_gpu_ipc_prepare(), then a second
  *      host barrier -- after which lbm_gpu_run() may be called (same n_steps on
  *      every rank).
- * The halo rows are written straight into the neighbours' HBM by the step kernel
+ * The ghost rows are written straight into the neighbours' HBM by the step kernel
  * (peer stores over NVLink) and ordered by device-side flags: no collective, no host
  * synchronisation per step.
+ *
+ * Failure and teardown.  lbm_gpu_run() returns only after both neighbours have completed
+ * the same number of kernel passes (a bounded device-side wait at the end of the run), so
+ * on return nothing is in flight towards this rank's window any more: destroying,
+ * uploading or re-creating needs no host barrier.  Every device-side wait for a neighbour
+ * is bounded (LBM_GPU_SYNC_TIMEOUT_MS, default 10000): if a neighbour never arrives -- its
+ * process died, or it was asked for a different n_steps -- the waiting rank gives up, raises
+ * an abort word in its neighbours so that the whole ring drains, and lbm_gpu_run() returns
+ * non-zero with the reason in lbm_gpu_last_error() (the reference's die() convention,
+ * d2q9-bgk.c:3001-3007).  The lattice of an abandoned run is void; further runs are refused.
  */
 #define LBM_GPU_IPC_DESC_BYTES 256
 int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows, int device,
@@ -139,6 +161,7 @@ int lbm_gpu_create_slab(const lbm_param* params, long long row0, long long nrows
                         unsigned flags, lbm_gpu** out);
 int lbm_gpu_ipc_export(lbm_gpu* h, void* desc /* LBM_GPU_IPC_DESC_BYTES */);
 int lbm_gpu_ipc_connect(lbm_gpu* h, const void* desc_below, const void* desc_above);
+int lbm_gpu_ipc_connect_all(lbm_gpu* h, const void* descs /* n x LBM_GPU_IPC_DESC_BYTES */, int n);
 int lbm_gpu_ipc_prepare(lbm_gpu* h);
 
 /*
@@ -213,7 +236,7 @@ void lbm_gpu_destroy(lbm_gpu* h);
 /* Text of the last error on this thread ("" if none). */
 const char* lbm_gpu_last_error(void);
 
-/* ABI version of this header. */
+/* ABI version of this header (2: lbm_gpu_ipc_connect_all, LBM_GPU_KERNEL_TB2, LBM_GPU_SYNC_EVENTS). */
 int lbm_gpu_abi_version(void);
 
 #ifdef __cplusplus

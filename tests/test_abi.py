@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(L.LIB_PATH)
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert L.load_library().lbm_gpu_abi_version() == 1
+    assert L.load_library().lbm_gpu_abi_version() == 2
 
 
 def test_no_torch_types_or_torch_linkage():

@@ -90,7 +90,7 @@ def test_slab_handles_refuse_a_shared_device():
         a.close(); b.close()
 
 
-@pytest.mark.parametrize("mode", ["events", "flags"])
+@pytest.mark.parametrize("mode", ["events", "flags", "default"])
 def test_real_multi_gpu_equals_single(mode):
     n = min(ndev(), 4)
     if n < 2:
@@ -98,12 +98,29 @@ def test_real_multi_gpu_equals_single(mode):
     nx, ny, steps = 512, 203, 40
     cells, obst = O.random_lattice(nx, ny, seed=1, p_obst=0.02)
     ref, av_ref, _ = single(nx, ny, cells, obst, steps)
-    flags = L.SYNC_FLAGS if mode == "flags" else 0
+    flags = {"flags": L.SYNC_FLAGS, "events": L.SYNC_EVENTS, "default": 0}[mode]
     with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, n_gpus=n, flags=flags) as lat:
         av = lat.run(steps)
         got = lat.download()
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     assert np.array_equal(av, av_ref)
+
+
+@pytest.mark.parametrize("mode", ["events", "flags"])
+def test_real_multi_gpu_two_step_kernel_equals_the_oracle(mode):
+    """K7 across GPUs: two-row ghost zones pushed over NVLink, passes ordered by flags / events."""
+    n = min(ndev(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nx, ny, steps = 1024, 203, 41
+    cells, obst = O.random_lattice(nx, ny, seed=4, p_obst=0.02)
+    ref, _, av_ref_d = O.run(cells, obst, steps, D, A, W)
+    flags = (L.SYNC_FLAGS if mode == "flags" else L.SYNC_EVENTS) | L.STRICT | L.KERNEL_TB2
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, n_gpus=n, flags=flags) as lat:
+        av = np.concatenate([lat.run(7), lat.run(steps - 7)])
+        got = lat.download()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
 
 
 WORKER = textwrap.dedent("""
@@ -118,41 +135,92 @@ WORKER = textwrap.dedent("""
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx, ny, steps = %(nx)d, %(ny)d, %(steps)d
+    nx, ny, steps, mode = %(nx)d, %(ny)d, %(steps)d, %(mode)r
     cells, obst = O.random_lattice(nx, ny, seed=1, p_obst=0.02)
     r0, k = L.split_rows(ny, world)[rank]
     lat = L.Lattice(nx, ny, 0.1, 0.005, 1.85, cells=cells[r0:r0 + k], obstacles=obst[r0:r0 + k],
-                    slab=(r0, k), device_ids=[local])
-    below, above = slabs.exchange_descriptors(lat.ipc_export(), rank, world, dist)
-    lat.ipc_connect(below, above)
+                    slab=(r0, k), device_ids=[local], flags=%(flags)d)
+    if mode == "pair":            # the two-descriptor form: one-step kernel
+        below, above = slabs.exchange_descriptors(lat.ipc_export(), rank, world, dist)
+        lat.ipc_connect(below, above)
+    else:                         # all descriptors: the library may pick the two-step kernel
+        lat.ipc_connect_all(slabs.gather_descriptors(lat.ipc_export(), world, dist))
     dist.barrier(); lat.ipc_prepare(); dist.barrier()
-    sums = np.concatenate([lat.run_sums(7), lat.run_sums(steps - 7)])
-    av = slabs.combine_step_sums(sums, lat.info().local_free_cells, dist, world)
-    np.save(os.path.join(%(out)r, "rows_%%d.npy" %% rank), lat.download())
-    if rank == 0:
-        np.save(os.path.join(%(out)r, "av.npy"), av)
-    dist.barrier()
+    if mode == "short" and rank == 1:
+        # this rank is asked for fewer steps: the others must give up, not hang
+        lat.run_sums(4)
+        open(os.path.join(%(out)r, "rank1_done"), "w").write("ok")
+    elif mode == "short":
+        import time
+        t0 = time.time()
+        try:
+            lat.run_sums(steps)
+            msg = "no error"
+        except L.LbmError as e:
+            msg = str(e)
+        open(os.path.join(%(out)r, "err_%%d.txt" %% rank), "w").write("%%.1f\\n%%s" %% (time.time() - t0, msg))
+    else:
+        sums = np.concatenate([lat.run_sums(7), lat.run_sums(steps - 7)])
+        av = slabs.combine_step_sums(sums, lat.info().local_free_cells, dist, world)
+        np.save(os.path.join(%(out)r, "rows_%%d.npy" %% rank), lat.download())
+        np.save(os.path.join(%(out)r, "kernel_%%d.npy" %% rank), np.array([lat.info().kernel]))
+        if rank == 0:
+            np.save(os.path.join(%(out)r, "av.npy"), av)
+            if mode == "all":     # connect_all also told the library the whole grid's free cells
+                np.save(os.path.join(%(out)r, "av_direct.npy"), lat.run(0))
+    if mode == "short":
+        dist.barrier()            # rank 1's window must outlive the passes its neighbours still run
+    # otherwise no barrier before close, on purpose: lbm_gpu_run returns only when the neighbours are done
     lat.close()
+    dist.barrier()
     dist.destroy_process_group()
 """)
 
 
-def test_one_process_per_gpu_over_ipc_equals_single(tmp_path):
-    n = min(ndev(), 4)
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    nx, ny, steps = 512, 203, 40
+def _launch(tmp_path, n, nx, ny, steps, mode, flags=0, env=None, timeout=600):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % {"root": ROOT, "nx": nx, "ny": ny, "steps": steps, "out": str(tmp_path)})
+    script.write_text(WORKER % {"root": ROOT, "nx": nx, "ny": ny, "steps": steps, "out": str(tmp_path), "mode": mode,
+                                "flags": flags})
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n,
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout,
+                          env=dict(os.environ, **(env or {})))
+
+
+@pytest.mark.parametrize("mode,nx,expect", [("pair", 512, "VEC4"), ("all", 512, "TB2"), ("all", 516 + 2, "VEC4")])
+def test_one_process_per_gpu_over_ipc_equals_single(tmp_path, mode, nx, expect):
+    n = min(ndev(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ny, steps = 203, 41
+    r = _launch(tmp_path, n, nx, ny, steps, mode)
     assert r.returncode == 0, r.stdout[-4000:]
     cells, obst = O.random_lattice(nx, ny, seed=1, p_obst=0.02)
-    ref, av_ref, _ = single(nx, ny, cells, obst, steps)
+    ref, av_ref, _ = single(nx, ny, cells, obst, steps, flags=L.KERNEL_VEC4)
     got = np.concatenate([np.load(os.path.join(str(tmp_path), "rows_%d.npy" % i)) for i in range(n)])
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     av = np.load(os.path.join(str(tmp_path), "av.npy"))
     # the sums are exact integers on the device; only the final double division differs
     np.testing.assert_allclose(av, av_ref.astype(np.float64), rtol=2e-7)
+    want = {"VEC4": L.KERNEL_VEC4, "TB2": L.KERNEL_TB2}[expect]
+    for i in range(n):
+        assert int(np.load(os.path.join(str(tmp_path), "kernel_%d.npy" % i))[0]) == want
+
+
+def test_a_rank_that_stops_early_makes_the_others_fail_not_hang(tmp_path):
+    """The flag protocol has an exit (the reference's convention is die(), d2q9-bgk.c:3001-3007):
+    rank 1 runs 4 steps, the others ask for 41 and must come back with an error within the
+    time-out instead of spinning inside a kernel for ever."""
+    n = min(ndev(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = _launch(tmp_path, n, 512, 203, 41, "short", env={"LBM_GPU_SYNC_TIMEOUT_MS": "2000"}, timeout=300)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert (tmp_path / "rank1_done").exists()
+    for i in range(n):
+        if i == 1:
+            continue
+        secs, msg = (tmp_path / ("err_%d.txt" % i)).read_text().split("\n", 1)
+        assert float(secs) < 60.0
+        assert "abandoned" in msg, msg

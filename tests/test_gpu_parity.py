@@ -132,7 +132,7 @@ def test_kernel_selection():
     with L.Lattice(4098, 4096, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_VEC4                # any width
     with L.Lattice(4096, 4096, DENSITY, ACCEL, OMEGA) as lat:
-        assert lat.info().kernel == L.KERNEL_VEC4
+        assert lat.info().kernel == L.KERNEL_TB2                 # two timesteps per pass (tests/test_gpu_tb2.py)
     nx, ny = 1024, 600          # more tiles than resident blocks: every block loops
     cells, obst = O.random_lattice(nx, ny, seed=13, p_obst=0.01)
     res = []
