@@ -60,6 +60,7 @@ struct CudaError {
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 constexpr int kPersistScalarBlocks = 296;      // measured, profiles/r01_small_grids.md
+constexpr long long kPersistMaxCells = 1536 * 1024;   // K5 while both buffers (72 B per cell) stay well inside the 126 MB L2
 constexpr size_t kStagingBytes = 64u << 20;   // device staging for AoS<->SoA / mask / fields
 
 // descriptor exchanged between processes (lbm_gpu_ipc_export / _connect)
@@ -443,8 +444,8 @@ class Grid : public GridBase {
     if (cap < 1) {
       if (want) throw CudaError{"cooperative launch is not available on this device"};
       kernel = saved;
-    } else if (!want && tiles > 4LL * cap) {
-      kernel = saved;             // large grid: bandwidth bound, one launch per step is free
+    } else if (!want && (long long)prm.nx * slabs[0].rows > kPersistMaxCells) {
+      kernel = saved;             // beyond L2: bandwidth bound, one launch per pass is free
     }
   }
 
@@ -470,7 +471,14 @@ class Grid : public GridBase {
       }
       tb2_strips = (prm.nx + LBM_TB2_MAX_WOUT - 1) / LBM_TB2_MAX_WOUT;
       tb2_wout = (int)round_up((prm.nx + tb2_strips - 1) / tb2_strips, 4);
-      tb2_seg_rows = 64;
+      // Segment height: every segment recomputes two rows of the first sub-step, so tall is
+      // cheap (64 rows: 3 %), but a grid should still be cut into at least ~6 waves of
+      // resident blocks or the last wave leaves SMs idle (4096^2: 64 rows = 1.3 waves).
+      int sms = 148, rows_max = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, slabs[0].device);
+      for (auto& s : slabs) rows_max = std::max(rows_max, s.rows);
+      const long long want_segs = (6LL * LBM_TB2_MIN_BLOCKS * sms + tb2_strips - 1) / tb2_strips;
+      tb2_seg_rows = (int)std::min<long long>(64, std::max<long long>(16, rows_max / std::max<long long>(1, want_segs)));
       if (const char* e = getenv("LBM_TB2_SEG_ROWS")) tb2_seg_rows = std::max(2, atoi(e));   // tuning knob
       tb2 = true;
       kernel = LBM_GPU_KERNEL_TB2;

@@ -33,13 +33,13 @@
 #define LBM_BLOCK_THREADS 128       // threads per block of K1a/K1b/K5
 #endif
 #ifndef LBM_MIN_BLOCKS
-#define LBM_MIN_BLOCKS 7            // K1a fp32: 7 blocks of 128 threads per SM = 72 registers, no spills,
-#endif                              // 896 threads/SM: +8.7 % over 3 x 256 threads at 80 registers
+#define LBM_MIN_BLOCKS 4            // K1a fp32: the packed collision wants ~100 registers; 7 blocks per SM (72
+#endif                              // registers) spill: 78.7 GLUPS against 93.9 at 4 blocks (profiles/r02_kernel_variants.md)
 #ifndef LBM_LOAD_MODE
 #define LBM_LOAD_MODE 0             // 0 plain, 1 ld.global.cs (evict-first), 2 ld.global.nc, 3 nc + L1::no_allocate
 #endif
 #ifndef LBM_PERSIST_MIN_BLOCKS
-#define LBM_PERSIST_MIN_BLOCKS 6    // K5: keeps it at <= 85 registers so 6 blocks/SM are resident
+#define LBM_PERSIST_MIN_BLOCKS 3    // K5: no spills; 1024^2 104 GLUPS against 75 at 6 blocks per SM (same file)
 #endif
 // Timing experiments that produce WRONG results exist only in builds made with
 // -DLBM_EXPERIMENTS (tools/build_variants.py); the shipped library cannot contain them.
@@ -522,9 +522,11 @@ __device__ __forceinline__ AvPair warp_reduce_fixed(const unsigned long long q) 
   const unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)(q & 0x3ffffffULL));
   const unsigned b = __reduce_add_sync(0xffffffffu, (unsigned)((q >> 26) & 0x3ffffffULL));
   const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)(q >> 52));
+  // a + b 2^26 + c 2^52 = lo + hi 2^32 with lo < 2^33: the accumulator words take millions of
+  // such pairs per step without wrapping
   AvPair r;
-  r.lo = (unsigned long long)a + ((unsigned long long)b << 26);
-  r.hi = (unsigned long long)c << 20;
+  r.lo = (unsigned long long)a + ((unsigned long long)(b & 0x3fu) << 26);
+  r.hi = (unsigned long long)(b >> 6) + ((unsigned long long)c << 20);
   return r;
 }
 

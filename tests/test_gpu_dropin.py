@@ -48,7 +48,8 @@ def test_reference_program_with_the_binding(name, tmp_path):
     # (serial float sum), we from the device's exact sum -> equal to float rounding
     re_ref = float(re.search(r"Reynolds number:\s+(\S+)", out_ref).group(1))
     re_ours = float(re.search(r"Reynolds number:\s+(\S+)", out_ours).group(1))
-    assert abs(re_ref - re_ours) <= 2e-6 * abs(re_ours)
+    # the reference adds 16 k speeds serially in fp32 (d2q9-bgk.c:2665-2714), the device sum is exact
+    assert abs(re_ref - re_ours) <= 1e-5 * abs(re_ours)
     # final_state: the reference's write_values on the downloaded lattice vs our device
     # fields -- same IEEE operations on the same values; only the obstacle column differs
     # where the reference's transposed index does (non-square 128x256)
