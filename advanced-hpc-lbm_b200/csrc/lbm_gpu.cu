@@ -122,6 +122,9 @@ struct Slab {
   size_t av_cap = 0;                  // steps
   void* staging = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;            // host <-> staging copies, overlapped with the kernels on `stream`
+  cudaEvent_t stage_filled[2] = {nullptr, nullptr};   // a staging half is ready for its consumer
+  cudaEvent_t stage_drained[2] = {nullptr, nullptr};  // ... and has been consumed
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t step_ev[2] = {nullptr, nullptr};   // "step t finished", alternating by parity
   long long free_cells = 0;
@@ -187,6 +190,11 @@ class Grid : public GridBase {
       window_free(s);
       if (s.ev0) cudaEventDestroy(s.ev0);
       if (s.ev1) cudaEventDestroy(s.ev1);
+      for (int i = 0; i < 2; i++) {
+        if (s.stage_filled[i]) cudaEventDestroy(s.stage_filled[i]);
+        if (s.stage_drained[i]) cudaEventDestroy(s.stage_drained[i]);
+      }
+      if (s.copy_stream) { cudaStreamSynchronize(s.copy_stream); cudaStreamDestroy(s.copy_stream); }
       for (int i = 0; i < 2; i++)
         if (s.step_ev[i]) cudaEventDestroy(s.step_ev[i]);
       if (s.stream) cudaStreamDestroy(s.stream);
@@ -262,6 +270,11 @@ class Grid : public GridBase {
     s.off_mask = off; off = round_up(off + maskb, 256);
     s.bytes = off;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&s.stage_filled[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&s.stage_drained[i], cudaEventDisableTiming));
+    }
     pool_alloc((void**)&s.base, s.bytes, s);
     for (int i = 0; i < 2; i++) {
       s.lattice[i] = (real*)(s.base + s.off_lattice[i]);
@@ -528,26 +541,39 @@ class Grid : public GridBase {
     unsigned long long* counter = s.sync + kScratch0;
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s.stream));
     if (obstacles) {
+      // host rows -> one half of the staging buffer (copy stream) -> packed into the mask
+      // (kernel stream); the copy of chunk i+1 overlaps the packing of chunk i, one
+      // synchronisation per call
       const bool bits = (flags & LBM_GPU_OBST_BITS) != 0;
       const int wpr = (nx + 31) / 32;
       const size_t row_bytes = bits ? (size_t)wpr * 4 : (size_t)nx * 4;
-      const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / row_bytes);
-      for (int r = 0; r < s.rows; r += chunk_rows) {
+      const size_t half = kStagingBytes / 2;
+      if (row_bytes > half) throw CudaError{"nx too large for the obstacle staging buffer"};
+      const int chunk_rows = (int)(half / row_bytes);
+      CK(cudaEventRecord(s.stage_drained[0], s.stream));       // orders the first copies behind the memsets above
+      CK(cudaEventRecord(s.stage_drained[1], s.stream));
+      int i = 0;
+      for (int r = 0; r < s.rows; r += chunk_rows, i++) {
         const int n = std::min(chunk_rows, s.rows - r);
-        CK(cudaMemcpyAsync(s.staging, (const char*)obstacles + (size_t)r * row_bytes, (size_t)n * row_bytes,
-                           cudaMemcpyHostToDevice, s.stream));
+        const int b = i & 1;
+        char* st = (char*)s.staging + (size_t)b * half;
+        CK(cudaStreamWaitEvent(s.copy_stream, s.stage_drained[b], 0));
+        CK(cudaMemcpyAsync(st, (const char*)obstacles + (size_t)r * row_bytes, (size_t)n * row_bytes,
+                           cudaMemcpyHostToDevice, s.copy_stream));
+        CK(cudaEventRecord(s.stage_filled[b], s.copy_stream));
+        CK(cudaStreamWaitEvent(s.stream, s.stage_filled[b], 0));
         if (bits) {
           const long long words = (long long)n * wpr;
           lbm::lbm_copy_mask_bits<<<(unsigned)((words + 255) / 256), 256, 0, s.stream>>>(
-              (const uint32_t*)s.staging, s.mask, mask_pitch, nx, r, n, counter);
+              (const uint32_t*)st, s.mask, mask_pitch, nx, r, n, counter);
         } else {
           const long long threads = (long long)n * wpr * 32;
           lbm::lbm_pack_mask<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
-              (const int*)s.staging, s.mask, mask_pitch, nx, r, n, counter);
+              (const int*)st, s.mask, mask_pitch, nx, r, n, counter);
         }
         CK(cudaGetLastError());
         launches++;
-        CK(cudaStreamSynchronize(s.stream));   // staging is reused by the next chunk
+        CK(cudaEventRecord(s.stage_drained[b], s.stream));
       }
     }
     unsigned long long blocked = 0;
@@ -993,33 +1019,54 @@ class Grid : public GridBase {
     }
   }
 
+  // Fields of rows [row0, row0+nrows): computed chunk by chunk into one half of the staging
+  // buffer (kernel stream) and copied out from the other half (copy stream): the kernel of
+  // chunk i+1 overlaps the device-to-host copies of chunk i, one synchronisation per call.
   void final_fields(long long row0, long long nrows, real* ux, real* uy, real* u, real* p) {
     const int nx = prm.nx;
     const size_t row_bytes = (size_t)nx * sizeof(real);
-    const int chunk_rows = (int)std::max<size_t>(1, kStagingBytes / (4 * row_bytes));
+    const size_t half = kStagingBytes / 2;
+    if (4 * row_bytes > half) throw CudaError{"nx too large for the fields staging buffer"};
+    const int chunk_rows = (int)(half / (4 * row_bytes));
+    std::vector<Slab<real>*> used;
     long long g = row0;
+    int i = 0;
     while (g < row0 + nrows) {
       Slab<real>& s = slab_of_row(g);
       CK(cudaSetDevice(s.device));
+      if (used.empty() || used.back() != &s) {
+        used.push_back(&s);
+        i = 0;
+      }
       const int n = (int)std::min<long long>({(long long)chunk_rows, s.row0 + s.rows - g, row0 + nrows - g});
       const long long ncells = (long long)n * nx;
-      real* st = (real*)s.staging;
+      const int b = i & 1;
+      real* st = (real*)((char*)s.staging + (size_t)b * half);
       real* d_ux = ux ? st : nullptr;
       real* d_uy = uy ? st + ncells : nullptr;
       real* d_u = u ? st + 2 * ncells : nullptr;
       real* d_p = p ? st + 3 * ncells : nullptr;
+      if (i >= 2) CK(cudaStreamWaitEvent(s.stream, s.stage_drained[b], 0));
       lbm::lbm_fields<real><<<(unsigned)((ncells + 255) / 256), 256, 0, s.stream>>>(
           s.lattice[cur], s.mask, plane_stride(s), pitch, mask_pitch, nx, (int)(g - s.row0), n,
           prm.density, d_ux, d_uy, d_u, d_p, nullptr);
       CK(cudaGetLastError());
       launches++;
+      CK(cudaEventRecord(s.stage_filled[b], s.stream));
+      CK(cudaStreamWaitEvent(s.copy_stream, s.stage_filled[b], 0));
       const size_t off = (size_t)(g - row0) * nx;
-      if (ux) CK(cudaMemcpyAsync(ux + off, d_ux, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
-      if (uy) CK(cudaMemcpyAsync(uy + off, d_uy, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
-      if (u) CK(cudaMemcpyAsync(u + off, d_u, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
-      if (p) CK(cudaMemcpyAsync(p + off, d_p, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.stream));
-      CK(cudaStreamSynchronize(s.stream));
+      if (ux) CK(cudaMemcpyAsync(ux + off, d_ux, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.copy_stream));
+      if (uy) CK(cudaMemcpyAsync(uy + off, d_uy, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.copy_stream));
+      if (u) CK(cudaMemcpyAsync(u + off, d_u, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.copy_stream));
+      if (p) CK(cudaMemcpyAsync(p + off, d_p, ncells * sizeof(real), cudaMemcpyDeviceToHost, s.copy_stream));
+      CK(cudaEventRecord(s.stage_drained[b], s.copy_stream));
       g += n;
+      i++;
+    }
+    for (Slab<real>* s : used) {
+      CK(cudaSetDevice(s->device));
+      CK(cudaStreamSynchronize(s->copy_stream));
+      CK(cudaStreamSynchronize(s->stream));
     }
   }
 

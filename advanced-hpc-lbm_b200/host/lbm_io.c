@@ -255,11 +255,11 @@ void lbm_write_final_state_rows(void* fpv, int nx, long long row0, long long nro
   size_t* lens = (size_t*)calloc((size_t)pieces, sizeof(size_t));
   if (bufs == NULL || lens == NULL) die("cannot allocate memory for output rows", __LINE__, __FILE__);
   int failed = 0;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) reduction(|:failed)
   for (long long p = 0; p < pieces; p++) {
     const long long rb = nrows * p / pieces, re = nrows * (p + 1) / pieces;
     bufs[p] = (char*)malloc((size_t)(re - rb) * (size_t)nx * LINE_MAX_BYTES + 1);
-    if (bufs[p] == NULL) { failed = 1; continue; }
+    if (bufs[p] == NULL) { failed |= 1; continue; }
     lens[p] = format_rows(bufs[p], nx, row0, rb, re, u_x, u_y, u, pressure, obstacle_bits);
   }
   if (failed) die("cannot allocate memory for output rows", __LINE__, __FILE__);

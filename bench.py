@@ -299,6 +299,32 @@ def _f64():
     return torch.float64
 
 
+def bind_near_gpu(local_rank):
+    """N > 1: keep this rank on the CPU cores next to its GPU (sysfs local_cpulist of the GPU's
+    PCI device), as an MPI launcher would.  The page-locked host buffers of the end-to-end
+    leg are then allocated on that NUMA node and eight GPUs do not push 43 GB per step
+    through one socket's memory.  LBM_BENCH_BIND=0 switches it off."""
+    if os.environ.get("LBM_BENCH_BIND", "1") == "0":
+        return "off"
+    try:
+        r = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=30)
+        bus = r.stdout.strip().lower()[-12:]
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no usable cores in " + spec
+        os.sched_setaffinity(0, cpus)
+        return "cores " + spec
+    except (OSError, ValueError, subprocess.SubprocessError) as e:
+        return "unavailable (%s)" % type(e).__name__
+
+
 KERNEL_NAMES = {4: "lbm_step_scalar", 16: "lbm_step_vec4", 64: "lbm_steps_persistent", 8: "lbm_step_tma",
                 256: "lbm_steps_cluster", 512: "lbm_step2_tb (two timesteps per pass) + lbm_step_vec4 for an odd step"}
 
@@ -348,16 +374,18 @@ def parity_leg(L, slabs, R):
         lat.close()
         return R.sum_array(sums), R.sum_u64(cs), R.sum(float(info.local_free_cells)), int(info.kernel)
 
-    for nx, want in ((515, 16), (1024, 512)):
+    # the two kernels of the headline path, named explicitly (a grid this small would otherwise
+    # take the L2-resident persistent kernel on one GPU): K1a for a ragged width, K7 otherwise
+    for nx, want in ((515, L.KERNEL_VEC4), (1024, L.KERNEL_TB2)):
         cells, obst = O.random_lattice(nx, ny, seed=1000 + nx + world, p_obst=0.02)
         obst[ny - 2, ::7] = 1
         case = {"nx": nx, "ny": ny}
         try:
-            sums, cs, free, kern = run_slabs(nx, cells, obst, L.STRICT)
+            sums, cs, free, kern = run_slabs(nx, cells, obst, L.STRICT | want)
             case["kernel"] = "%s<float, STRICT, MULTI=%s>" % (KERNEL_NAMES.get(kern, str(kern)), "true" if world > 1 else "false")
             if kern != want:
                 fail("nx=%d: expected kernel %d, the library chose %d" % (nx, want, kern))
-            fsums, fcs, _, _ = run_slabs(nx, cells, obst, 0)
+            fsums, fcs, _, _ = run_slabs(nx, cells, obst, want)
             if rank == 0:
                 ref, _, av_ref = O.run(cells, obst, steps, D, A, W)
                 case["checksum"] = "%016x" % cs
@@ -476,6 +504,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
 
+    binding = bind_near_gpu(local_rank) if world > 1 else "not needed (1 GPU)"
     import lbm_b200 as L
     slabs = __import__("importlib").import_module("advanced-hpc-lbm_b200.slabs")
     R = Ranks(rank, local_rank, world)
@@ -658,7 +687,7 @@ def main():
         "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": dict(workload_config(args, world), cpu_binding=binding),
         "achieved_hbm_gbs_per_gpu": achieved,
         "wall_ms_per_step": 1e3 * wall_s / K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
