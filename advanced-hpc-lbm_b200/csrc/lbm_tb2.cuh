@@ -60,6 +60,7 @@ struct Tb2Args {
   const uint32_t* ghost_mask;      // own window: mask words of row -1, then of row `rows`
   unsigned long long* av2;         // sums of sub-step 2
   int wout;                        // owned columns per strip (multiple of 4, <= LBM_TB2_MAX_WOUT)
+  int span;                        // staged columns per strip = threads x 4: 512, or nx + 8 for a narrow grid
   int seg_rows;                    // rows per segment
 };
 
@@ -89,22 +90,29 @@ __device__ __forceinline__ const float* tb2_row_ptr(const StepArgs<float>& a, co
 }
 
 // warp 0: start the copies of the nine plane-rows that sub-step 1 on row r pulls from -- lane
-// 0 announces the bytes, lanes 0..8 each work out where "their" plane-row lives and copy it
+// 0 announces the bytes, lanes 0..8 each work out where "their" plane-row lives and copy it,
+// in as many pieces as the periodic wrap in x cuts the span into (up to three when the span
+// is the whole width plus halo)
 __device__ __forceinline__ void tb2_issue(const StepArgs<float>& a, Tb2Smem& sm, const int stage, const int r,
-                                          const int s0, const int lane) {
+                                          const int s0, const int span, const int lane) {
   unsigned long long* bar = &sm.mbar[stage];
   if (lane == 0)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"((uint32_t)(9 * LBM_TB2_SPAN * sizeof(float))) : "memory");
+                 "r"((uint32_t)(9 * span * sizeof(float))) : "memory");
   __syncwarp();
   if (lane < 9) {
     const int k = lane;
-    const int first = min(LBM_TB2_SPAN, a.nx - s0);            // columns before the periodic wrap in x
     const int dy = (k == 2 || k == 5 || k == 6) ? -1 : (k == 4 || k == 7 || k == 8) ? 1 : 0;
     const float* row = tb2_row_ptr(a, k, r + dy);
     float* dst = &sm.in[stage][k][LBM_TB2_PAD];
-    tb2_bulk_load(dst, row + s0, (uint32_t)first * 4u, bar);
-    if (first < LBM_TB2_SPAN) tb2_bulk_load(dst + first, row, (uint32_t)(LBM_TB2_SPAN - first) * 4u, bar);
+    int col = s0, left = span;
+    while (left > 0) {
+      const int n = min(left, a.nx - col);
+      tb2_bulk_load(dst, row + col, (uint32_t)n * 4u, bar);
+      dst += n;
+      left -= n;
+      col = 0;
+    }
   }
 }
 
@@ -125,46 +133,30 @@ __device__ __forceinline__ void tb2_put(float* row, const int c0, const float (&
   *reinterpret_cast<float4*>(row + LBM_TB2_PAD + c0) = make_float4(o[0][k], o[1][k], o[2][k], o[3][k]);
 }
 
-template <bool STRICT, bool MULTI>
-__global__ void __launch_bounds__(LBM_TB2_THREADS, LBM_TB2_MIN_BLOCKS)
-lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
-  extern __shared__ __align__(128) unsigned char tb2_smem_raw[];
-  Tb2Smem& sm = *reinterpret_cast<Tb2Smem*>(tb2_smem_raw);
+// One tile = one strip x one segment, two timesteps.  `phases` holds the parity each staging
+// barrier completes next (a block that works through several tiles keeps using the barriers).
+template <bool STRICT>
+__device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const int strip, const int seg,
+                                         uint32_t& phases, unsigned long long& q1, unsigned long long& q2,
+                                         bool& bad1, bool& bad2) {
   const StepArgs<float>& a = ta.s;
   const int tid = threadIdx.x;
-  int strip, seg;
-  tile_of_block(a.tiles_x, a.tiles_y, 1, strip, seg);
-  const bool is_boundary = is_edge_tile(seg, a.tiles_y, 1);
-
   const int X0 = strip * ta.wout;                              // first owned column
   const int S0 = (X0 >= LBM_TB2_PAD) ? X0 - LBM_TB2_PAD : X0 - LBM_TB2_PAD + a.nx;   // first staged column
   const int R0 = seg * ta.seg_rows;
   const int R1 = min(R0 + ta.seg_rows, a.rows);
   const int n_it = R1 - R0 + 2;                                // sub-step-1 rows R0-1 .. R1
 
-  const int c0 = 4 * tid;                                      // the quad's column inside the span
+  // the quad's column inside the span (threads beyond the span idle along on its last quad)
+  const int c0 = min(4 * tid, ta.span - 4);
   int xg = S0 + c0;                                            // ... and in the grid (nx % 4 == 0: no straddling)
-  if (xg >= a.nx) xg -= a.nx;
-  const bool owned = (tid >= 1) && (c0 - LBM_TB2_PAD < ta.wout) && (X0 + c0 - LBM_TB2_PAD < a.nx);
+  while (xg >= a.nx) xg -= a.nx;
+  const bool owned = (tid >= 1) && (4 * tid < ta.span) && (c0 - LBM_TB2_PAD < ta.wout) &&
+                     (X0 + c0 - LBM_TB2_PAD < a.nx);
 
-  // pads of the staged rows are never written by the copies or the ring stores: the edge
-  // quads of the span read them (their results are never used), keep them defined
-  for (int i = tid; i < 35 * 2 * LBM_TB2_PAD; i += LBM_TB2_THREADS) {
-    float* row = &sm.in[0][0][0] + (size_t)(i / (2 * LBM_TB2_PAD)) * LBM_TB2_ROWF;
-    const int e = i % (2 * LBM_TB2_PAD);
-    row[e < LBM_TB2_PAD ? e : LBM_TB2_PAD + LBM_TB2_SPAN + (e - LBM_TB2_PAD)] = 0.f;
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[0])) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[1])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  cudaGridDependencySynchronize();           // PDL: the previous pass's writes are visible from here on
-  __syncthreads();
-  boundary_wait<float, MULTI>(a, is_boundary);
   if (tid < 32) {
 #pragma unroll 1
-    for (int k = 0; k < 2; k++) tb2_issue(a, sm, k, R0 - 1 + k, S0, tid);
+    for (int k = 0; k < 2; k++) tb2_issue(a, sm, k, R0 - 1 + k, S0, ta.span, tid);
   }
 
   const QuadConsts<float, STRICT> qc(a.omega);
@@ -176,8 +168,6 @@ lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
   };
   uint32_t mbits = mask_bits(R0 - 1);        // mask of the row sub-step 1 works on
   uint32_t mbits_prev = 0u;                  // ... and of the row before it (sub-step 2's row)
-  unsigned long long q1 = 0ULL, q2 = 0ULL;
-  bool bad1 = false, bad2 = false;
 
 #pragma unroll 1
   for (int i = 0; i < n_it; i++) {
@@ -187,7 +177,8 @@ lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
     float keep4[4];
     {
       // ---------------- sub-step 1 on row r: pulled values are staged in sm.in[st] ----------
-      tb2_mbar_wait(&sm.mbar[st], (uint32_t)((i >> 1) & 1));
+      tb2_mbar_wait(&sm.mbar[st], (phases >> st) & 1u);
+      phases ^= 1u << st;
       float in[4][9], out[4][9];
       const float(*row)[LBM_TB2_ROWF] = sm.in[st];
       tb2_get(row[0], c0, in[0][0], in[1][0], in[2][0], in[3][0]);
@@ -220,7 +211,7 @@ lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
       for (int j = 0; j < 4; j++) keep4[j] = out[j][4];
     }
     __syncthreads();          // ring rows of this iteration are complete; stage `st` has been read by everyone
-    if (tid < 32 && i + 2 < n_it) tb2_issue(a, sm, st, r + 2, S0, tid);
+    if (tid < 32 && i + 2 < n_it) tb2_issue(a, sm, st, r + 2, S0, ta.span, tid);
 
     if (i >= 2) {
       // ---------------- sub-step 2 on row y = r - 1, pulling sub-step-1 rows y-1, y, y+1 ----
@@ -284,12 +275,112 @@ lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
     __syncthreads();          // the ring rows read above are overwritten by the next iteration
   }
 
+}
+
+// shared memory of a block before its first tile: staging barriers, and the pads of the staged
+// rows -- never written by the copies or the ring stores, read by the edge quads of the span
+// (whose results are never used): keep them defined
+__device__ __forceinline__ void tb2_init_smem(Tb2Smem& sm, const int span) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 35 * 2 * LBM_TB2_PAD; i += blockDim.x) {
+    float* row = &sm.in[0][0][0] + (size_t)(i / (2 * LBM_TB2_PAD)) * LBM_TB2_ROWF;
+    const int e = i % (2 * LBM_TB2_PAD);
+    row[e < LBM_TB2_PAD ? e : span + e] = 0.f;
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K7  lbm_step2_tb: one launch = two timesteps of one slab (grids beyond L2, any GPU count)
+// ------------------------------------------------------------------------------------
+template <bool STRICT, bool MULTI>
+__global__ void __launch_bounds__(LBM_TB2_THREADS, LBM_TB2_MIN_BLOCKS)
+lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
+  extern __shared__ __align__(128) unsigned char tb2_smem_raw[];
+  Tb2Smem& sm = *reinterpret_cast<Tb2Smem*>(tb2_smem_raw);
+  const StepArgs<float>& a = ta.s;
+  int strip, seg;
+  tile_of_block(a.tiles_x, a.tiles_y, 1, strip, seg);
+  const bool is_boundary = is_edge_tile(seg, a.tiles_y, 1);
+  tb2_init_smem(sm, ta.span);
+  cudaGridDependencySynchronize();           // PDL: the previous pass's writes are visible from here on
+  __syncthreads();
+  boundary_wait<float, MULTI>(a, is_boundary);
+  uint32_t phases = 0u;
+  unsigned long long q1 = 0ULL, q2 = 0ULL;
+  bool bad1 = false, bad2 = false;
+  tb2_tile<STRICT>(ta, sm, strip, seg, phases, q1, q2, bad1, bad2);
   if (bad1) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
   if (bad2) atomicOr(ta.av2 + 1, LBM_NONFINITE_MARK);
   block_accumulate(q1, a.av);
   __syncthreads();            // block_accumulate's shared scratch is reused
   block_accumulate(q2, ta.av2);
   boundary_signal<float, MULTI>(a, is_boundary);
+}
+
+// ------------------------------------------------------------------------------------
+// K8  lbm_steps_tb2_persistent: ALL timestep pairs of a run in one cooperative launch, for
+// grids that live in L2 (the reference's shipped inputs).  K5 pays one grid barrier and one
+// dependent L2 round trip per TIMESTEP; here a block keeps the intermediate step in shared
+// memory and meets the others once per TWO timesteps.  Single slab (the ghost rows are the
+// slab's own); every block owns a fixed set of tiles; the buffers swap roles inside the
+// kernel.  Must be launched with cudaLaunchCooperativeKernel so that all blocks are resident.
+// ------------------------------------------------------------------------------------
+struct Tb2PersistArgs {
+  Tb2Args t;                   // geometry and constants; the per-pass pointers are set inside the kernel
+  float* lattice[2];
+  float* side[2];
+  float* window;               // own window: ghost rows at ghost_offset(pitch, parity, direction)
+  unsigned long long* av;      // 2 x n_passes steps x LBM_AV_SLOTS x LBM_AV_STRIDE words
+  unsigned long long* barrier; // zeroed before the launch
+  int first_parity;            // buffer index read by the first pass
+  int n_passes;
+  int n_tiles;
+};
+
+template <bool STRICT>
+__global__ void __launch_bounds__(LBM_TB2_THREADS, LBM_TB2_MIN_BLOCKS)
+lbm_steps_tb2_persistent(const __grid_constant__ Tb2PersistArgs pa) {
+  extern __shared__ __align__(128) unsigned char tb2_smem_raw[];
+  Tb2Smem& sm = *reinterpret_cast<Tb2Smem*>(tb2_smem_raw);
+  Tb2Args ta = pa.t;
+  StepArgs<float>& a = ta.s;
+  const int pitch = a.pitch;
+  tb2_init_smem(sm, ta.span);
+  __syncthreads();
+  uint32_t phases = 0u;
+  for (int p = 0; p < pa.n_passes; p++) {
+    const int src = (pa.first_parity + p) & 1, dst = src ^ 1;
+    a.src = pa.lattice[src];
+    a.dst = pa.lattice[dst];
+    a.side_src = pa.side[src];
+    a.side_dst = pa.side[dst];
+    a.ghost_s = pa.window + ghost_offset(pitch, src, 0);
+    a.ghost_n = pa.window + ghost_offset(pitch, src, 1);
+    a.push_up = pa.window + ghost_offset(pitch, dst, 0);
+    a.push_dn = pa.window + ghost_offset(pitch, dst, 1);
+    a.av = pa.av + (size_t)(2 * p) * (LBM_AV_STRIDE * LBM_AV_SLOTS);
+    ta.av2 = a.av + LBM_AV_STRIDE * LBM_AV_SLOTS;
+    unsigned long long q1 = 0ULL, q2 = 0ULL;
+    bool bad1 = false, bad2 = false;
+    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
+      const int seg = tile / a.tiles_x;
+      tb2_tile<STRICT>(ta, sm, tile - seg * a.tiles_x, seg, phases, q1, q2, bad1, bad2);
+    }
+    if (bad1) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
+    if (bad2) atomicOr(ta.av2 + 1, LBM_NONFINITE_MARK);
+    warp_accumulate(q1, a.av);
+    warp_accumulate(q2, ta.av2);
+    // what this block stored (generic proxy) is read by other blocks' bulk copies (async proxy)
+    // after the barrier: order the two proxies on both sides of it
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    grid_barrier(pa.barrier, (unsigned long long)gridDim.x * (unsigned long long)(p + 1));
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  }
 }
 
 }  // namespace lbm

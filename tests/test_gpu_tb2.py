@@ -1,4 +1,6 @@
-"""K7, the two-timesteps-per-pass kernel (temporal blocking), through the C-ABI.
+"""K7 and K8, the two-timesteps-per-pass kernels (temporal blocking), through the C-ABI.
+K7: one launch per pair of timesteps, any GPU count; K8: its persistent single-GPU form for
+grids that live in L2 (one grid barrier per pair of timesteps).
 
 Two iterations of the reference's loop (d2q9-bgk.c:180-201) fused into one pass over HBM
 must give what two separate iterations give:
@@ -31,17 +33,36 @@ def seg_rows(monkeypatch):
     return set_rows
 
 
-@pytest.mark.parametrize("nx,ny", [(512, 8), (520, 11), (1024, 17), (1540, 12), (2048, 70), (516, 130), (1008, 9)])
+TWO_STEP = [L.KERNEL_TB2, L.KERNEL_TB2_PERSISTENT]
+
+
+@pytest.mark.parametrize("nx,ny", [(512, 8), (520, 11), (1024, 17), (1540, 12), (2048, 70), (516, 130), (1008, 9),
+                                   (32, 8), (128, 128), (128, 256), (256, 37), (504, 9), (508, 10), (36, 300)])
 @pytest.mark.parametrize("steps", [1, 2, 3, 10])
-def test_strict_bit_exact(nx, ny, steps):
+@pytest.mark.parametrize("kernel", TWO_STEP)
+def test_strict_bit_exact(nx, ny, steps, kernel):
     cells, obst = O.random_lattice(nx, ny, seed=nx * 1000 + ny)
     ref, _, av_ref_d = O.run(cells, obst, steps, D, A, W)
-    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.STRICT | L.KERNEL_TB2) as lat:
-        assert lat.info().kernel == L.KERNEL_TB2
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.STRICT | kernel) as lat:
+        assert lat.info().kernel == kernel
         av = lat.run(steps)
         got = lat.download()
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), \
         "%dx%d: %d cells differ" % (nx, ny, np.count_nonzero((got != ref).any(axis=2)))
+    np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
+
+
+@pytest.mark.parametrize("rows_per_tile", [1, 2, 3, 7, 40])
+def test_persistent_form_every_tile_height(rows_per_tile, monkeypatch):
+    """K8 with more tiles than resident blocks (every block loops) and with one-row tiles."""
+    monkeypatch.setenv("LBM_TB2P_SEG_ROWS", str(rows_per_tile))
+    nx, ny, steps = 1024, 600 if rows_per_tile == 1 else 45, 7
+    cells, obst = O.random_lattice(nx, ny, seed=rows_per_tile, p_obst=0.02)
+    ref, _, av_ref_d = O.run(cells, obst, steps, D, A, W)
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.STRICT | L.KERNEL_TB2_PERSISTENT) as lat:
+        av = np.concatenate([lat.run(3), lat.run(steps - 3)])
+        got = lat.download()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
 
 
@@ -58,34 +79,36 @@ def test_every_segment_height(rows_per_segment, seg_rows):
     np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
 
 
-@pytest.mark.parametrize("nx,ny", [(512, 16), (1024, 40), (2052, 33)])
+@pytest.mark.parametrize("nx,ny", [(512, 16), (1024, 40), (2052, 33), (128, 128)])
 def test_default_build_gives_the_bits_of_the_one_step_kernel(nx, ny):
     steps = 21
     cells, obst = O.random_lattice(nx, ny, seed=3, p_obst=0.02)
     res = []
-    for k in (L.KERNEL_VEC4, L.KERNEL_TB2):
+    for k in (L.KERNEL_VEC4, L.KERNEL_TB2, L.KERNEL_TB2_PERSISTENT):
         with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=k) as lat:
             av = lat.run(steps)
             res.append((lat.download(), av, lat.final_fields()))
-    assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))
-    assert np.array_equal(res[0][1], res[1][1])
-    for a, b in zip(res[0][2], res[1][2]):
-        assert np.array_equal(a, b)
+    for other in res[1:]:
+        assert np.array_equal(res[0][0].view(np.uint32), other[0].view(np.uint32))
+        assert np.array_equal(res[0][1], other[1])
+        for a, b in zip(res[0][2], other[2]):
+            assert np.array_equal(a, b)
     ref, _, av_ref_d = O.run(cells, obst, steps, D, A, W)
     rel = np.abs(res[1][0].astype(np.float64) - ref) / np.abs(ref)
     assert rel.max() <= 2e-5
     np.testing.assert_allclose(res[1][1].astype(np.float64), av_ref_d, rtol=1e-5, atol=0)
 
 
-def test_chunked_runs_equal_one_run():
+@pytest.mark.parametrize("kernel", TWO_STEP)
+def test_chunked_runs_equal_one_run(kernel):
     """run(a); run(b) == run(a+b) for odd and even pieces: a lone step between two-step passes
     keeps the two-row ghost zones filled."""
     nx, ny = 1024, 24
     cells, obst = O.random_lattice(nx, ny, seed=11)
-    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.KERNEL_TB2) as lat:
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=kernel) as lat:
         av_all = lat.run(12)
         one = lat.download()
-    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.KERNEL_TB2) as lat:
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=kernel) as lat:
         av_parts = np.concatenate([lat.run(1), lat.run(3), lat.run(0), lat.run(5), lat.run(2), lat.run(1)])
         parts = lat.download()
     assert np.array_equal(one, parts)
@@ -125,11 +148,17 @@ def test_selection_and_refusals():
     with L.Lattice(4098, 4096, D, A, W) as lat:
         assert lat.info().kernel == L.KERNEL_VEC4                # the bulk copies need nx % 4 == 0
     with L.Lattice(1024, 1024, D, A, W) as lat:
-        assert lat.info().kernel == L.KERNEL_PERSISTENT          # lives in L2
+        assert lat.info().kernel == L.KERNEL_TB2_PERSISTENT      # lives in L2: one barrier per two timesteps
+    with L.Lattice(1022, 1024, D, A, W) as lat:
+        assert lat.info().kernel == L.KERNEL_PERSISTENT          # ... ragged width: one barrier per timestep
+    with L.Lattice(1024, 1024, D, A, W, f64=True) as lat:
+        assert lat.info().kernel == L.KERNEL_PERSISTENT
     with pytest.raises(L.LbmError, match="two-step kernel"):
         L.Lattice(130, 64, D, A, W, flags=L.KERNEL_TB2)
     with pytest.raises(L.LbmError, match="two-step kernel"):
         L.Lattice(512, 6, D, A, W, flags=L.KERNEL_TB2)
+    with pytest.raises(L.LbmError, match="two-step kernel"):
+        L.Lattice(512, 32, D, A, W, flags=L.KERNEL_TB2_PERSISTENT, n_gpus=2, device_ids=[0, 0])
     with pytest.raises(L.LbmError, match="two-step kernel"):
         L.Lattice(512, 20, D, A, W, flags=L.KERNEL_TB2, n_gpus=3, device_ids=[0, 0, 0])   # 6-7 rows per slab
 
@@ -145,26 +174,27 @@ def test_blown_up_lattice_reports_nan():
 
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large],
           derandomize=True)
-@given(nxq=st.integers(128, 300), ny=st.integers(8, 40), steps=st.integers(1, 7), seed=st.integers(0, 10 ** 6),
+@given(nxq=st.integers(8, 300), ny=st.integers(8, 40), persistent=st.booleans(), steps=st.integers(1, 7), seed=st.integers(0, 10 ** 6),
        p_obst=st.sampled_from([0.0, 0.02, 0.2]), slabs=st.integers(1, 3), density=st.sampled_from([0.1, 0.37]),
        accel=st.sampled_from([0.005, 0.05, 1.1]), omega=st.sampled_from([0.7, 1.0, 1.85]), split=st.integers(0, 7),
        walls=st.booleans(), seg=st.sampled_from([2, 3, 4, 9, 64]))
-def test_any_configuration_matches_the_oracle(nxq, ny, steps, seed, p_obst, slabs, density, accel, omega, split,
-                                              walls, seg):
+def test_any_configuration_matches_the_oracle(nxq, ny, persistent, steps, seed, p_obst, slabs, density, accel, omega,
+                                              split, walls, seg):
     nx = 4 * nxq
-    n = slabs if ny // slabs >= 8 else 1
-    os.environ["LBM_TB2_SEG_ROWS"] = str(seg)
+    n = slabs if (ny // slabs >= 8 and not persistent) else 1
+    kernel = L.KERNEL_TB2_PERSISTENT if persistent else L.KERNEL_TB2
+    os.environ["LBM_TB2_SEG_ROWS"] = os.environ["LBM_TB2P_SEG_ROWS"] = str(seg)
     try:
         cells, obst = O.random_lattice(nx, ny, seed=seed, density=density, p_obst=p_obst, walls=walls)
         ref, _, av_ref = O.run(cells, obst, steps, density, accel, omega)
         first = min(split, steps)
-        with L.Lattice(nx, ny, density, accel, omega, cells=cells, obstacles=obst, flags=L.STRICT | L.KERNEL_TB2,
+        with L.Lattice(nx, ny, density, accel, omega, cells=cells, obstacles=obst, flags=L.STRICT | kernel,
                        n_gpus=n, device_ids=[0] * n) as lat:
             av = np.concatenate([lat.run(first), lat.run(steps - first)])
             got = lat.download()
             _, cs = lat.digest()
     finally:
-        del os.environ["LBM_TB2_SEG_ROWS"]
+        del os.environ["LBM_TB2_SEG_ROWS"], os.environ["LBM_TB2P_SEG_ROWS"]
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     assert cs == L.lattice_checksum(ref)
     ok = np.isfinite(av_ref)
