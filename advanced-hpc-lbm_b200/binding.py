@@ -27,7 +27,6 @@ POOL = 128
 KERNEL_CLUSTER = 256
 KERNEL_TB2 = 512
 SYNC_EVENTS = 1024
-KERNEL_TB2_PERSISTENT = 2048
 IPC_DESC_BYTES = 256
 
 

@@ -169,7 +169,6 @@ class Grid : public GridBase {
   int cur = 0;                 // lattice buffer / window parity holding the current state (flips per pass)
   bool tb2 = false;            // two timesteps per pass (K7) wherever two steps remain
   int tb2_strips = 0, tb2_wout = 0, tb2_seg_rows = 0, tb2_span = 0, tb2_threads = 0;
-  int tb2p_seg_rows = 0;       // K8: segment height, chosen so that every resident block gets one tile
   bool failed = false;         // a neighbour never arrived: the lattice contents are void
   unsigned long long timeout_ns = 10000000000ULL;
   long long launches = 0;
@@ -344,7 +343,7 @@ class Grid : public GridBase {
     if (flags & LBM_GPU_KERNEL_SCALAR) kernel = LBM_GPU_KERNEL_SCALAR;
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
-    else if (flags & (LBM_GPU_KERNEL_TB2 | LBM_GPU_KERNEL_TB2_PERSISTENT)) kernel = LBM_GPU_KERNEL_VEC4;   // decided in choose_tb2()
+    else if (flags & LBM_GPU_KERNEL_TB2) kernel = LBM_GPU_KERNEL_VEC4;         // decided in choose_tb2()
     else if (flags & LBM_GPU_KERNEL_CLUSTER) kernel = LBM_GPU_KERNEL_VEC4;     // decided in choose_kernel()
     else kernel = LBM_GPU_KERNEL_VEC4;                         // refined in choose_kernel()
     if (flags & LBM_GPU_KERNEL_TMA) {
@@ -425,8 +424,7 @@ class Grid : public GridBase {
 
   void choose_kernel() {
     const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT |
-                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER | LBM_GPU_KERNEL_TB2 |
-                                 LBM_GPU_KERNEL_TB2_PERSISTENT);
+                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER | LBM_GPU_KERNEL_TB2);
     // K6 is opt-in only: 16 SMs doing all the arithmetic are no faster than K5 spreading it
     // over the whole chip (profiles/r01_small_grids.md).
     if (flags & LBM_GPU_KERNEL_CLUSTER) {
@@ -476,15 +474,12 @@ class Grid : public GridBase {
     return (prm.nx % 4 == 0) && prm.nx >= 32 && rows_min >= kTb2MinRows;
   }
 
-  bool tb2_possible_forced(int rows_min) const { return tb2_possible(rows_min); }
-
   void enable_tb2() {
     if constexpr (sizeof(real) == 4) {
       for (auto& s : slabs) {
         CK(cudaSetDevice(s.device));
         for (const void* fn : {(const void*)lbm::lbm_step2_tb<false, false>, (const void*)lbm::lbm_step2_tb<false, true>,
-                               (const void*)lbm::lbm_step2_tb<true, false>, (const void*)lbm::lbm_step2_tb<true, true>,
-                               (const void*)lbm::lbm_steps_tb2_persistent<false>, (const void*)lbm::lbm_steps_tb2_persistent<true>})
+                               (const void*)lbm::lbm_step2_tb<true, false>, (const void*)lbm::lbm_step2_tb<true, true>})
           CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lbm::Tb2Smem)));
       }
       if (prm.nx + 2 * LBM_TB2_PAD <= LBM_TB2_SPAN) {      // narrow grid: one strip, the whole width plus halo
@@ -523,45 +518,14 @@ class Grid : public GridBase {
     }
   }
 
-  const void* tb2p_fn() const {
-    if constexpr (sizeof(real) == 4)
-      return (flags & LBM_GPU_STRICT) ? (const void*)lbm::lbm_steps_tb2_persistent<true>
-                                      : (const void*)lbm::lbm_steps_tb2_persistent<false>;
-    return nullptr;
-  }
-  int tb2p_capacity(const Slab<real>& s) {
-    int per_sm = 0, sms = 0, coop = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb2p_fn(), tb2_threads, sizeof(lbm::Tb2Smem)));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
-    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
-    return coop ? per_sm * sms : 0;
-  }
-
-  // single-process form: decide once all slabs exist.  Grids beyond L2 (not taken by the
-  // persistent kernel K5) get K7; L2-resident single-GPU grids get K8, its persistent form.
+  // single-process form: decide once all slabs exist
   void choose_tb2() {
     int rows_min = slabs[0].rows;
     for (auto& s : slabs) rows_min = std::min(rows_min, s.rows);
-    const bool want = (flags & LBM_GPU_KERNEL_TB2) != 0, want_p = (flags & LBM_GPU_KERNEL_TB2_PERSISTENT) != 0;
+    const bool want = (flags & LBM_GPU_KERNEL_TB2) != 0;
     const bool big = (kernel == LBM_GPU_KERNEL_VEC4);        // not taken by the persistent kernel
-    const bool small = (kernel == LBM_GPU_KERNEL_PERSISTENT) && !(flags & LBM_GPU_KERNEL_PERSISTENT);
-    const bool ok = tb2_possible(rows_min) || ((want || want_p) && tb2_possible_forced(rows_min));
-    static const bool no_k8 = getenv("LBM_GPU_NO_TB2P") && getenv("LBM_GPU_NO_TB2P")[0] == '1';
-    if (ok && (want_p || (small && !want && !no_k8)) && slabs.size() == 1 && !slab_mode) {
-      enable_tb2();
-      CK(cudaSetDevice(slabs[0].device));
-      const int cap = tb2p_capacity(slabs[0]);
-      if (cap < 1) throw CudaError{"cooperative launch is not available on this device"};
-      // one tile per resident block if the grid is large enough; otherwise one row per tile
-      tb2p_seg_rows = std::max(1, (int)((slabs[0].rows + cap / tb2_strips - 1) / std::max(1, cap / tb2_strips)));
-      if (const char* e = getenv("LBM_TB2P_SEG_ROWS")) tb2p_seg_rows = std::max(1, atoi(e));   // tuning knob
-      kernel = LBM_GPU_KERNEL_TB2_PERSISTENT;
-    } else if (ok && (want || big)) {
-      enable_tb2();
-    } else if (want || want_p) {
-      throw CudaError{"the two-step kernel needs fp32, nx a multiple of 4 and >= 32, >= 8 rows per slab (and a "
-                      "single GPU for its persistent form)"};
-    }
+    if (tb2_possible(rows_min) && (want || big)) enable_tb2();
+    else if (want) throw CudaError{"the two-step kernel needs fp32, nx a multiple of 4 and >= 32, and >= 8 rows per slab"};
   }
 
   // ------------------------------------------------------------- lattice input ----
@@ -948,43 +912,6 @@ class Grid : public GridBase {
       CK(cudaLaunchCooperativeKernel(persistent_fn(), dim3(nblocks), dim3(bx, by), kargs, 0, s.stream));
       launches++;
       cur = (cur + n_steps) & 1;
-    } else if (kernel == LBM_GPU_KERNEL_TB2_PERSISTENT) {
-      const int n_passes = n_steps / 2;
-      if constexpr (sizeof(real) == 4) {
-        if (n_passes > 0) {
-          Slab<real>& s = slabs[0];
-          CK(cudaSetDevice(s.device));
-          lbm::Tb2PersistArgs pa;
-          memset(&pa, 0, sizeof pa);
-          fill_step_args(pa.t.s, s, 0);
-          lbm::StepArgs<real>& a = pa.t.s;
-          const int nsegs = (s.rows + tb2p_seg_rows - 1) / tb2p_seg_rows;
-          a.tiles_x = tb2_strips;
-          a.tiles_y = nsegs;
-          a.deep = 1;
-          pa.t.ghost_mask = s.ghost_mask;
-          pa.t.wout = tb2_wout;
-          pa.t.span = tb2_span;
-          pa.t.seg_rows = tb2p_seg_rows;
-          for (int b = 0; b < 2; b++) { pa.lattice[b] = s.lattice[b]; pa.side[b] = s.side[b]; }
-          pa.window = (real*)s.win;
-          pa.av = s.av;
-          pa.barrier = s.sync + kGridBarrier;
-          pa.first_parity = cur;
-          pa.n_passes = n_passes;
-          pa.n_tiles = tb2_strips * nsegs;
-          const int cap = tb2p_capacity(s);
-          const int rounds = (pa.n_tiles + cap - 1) / cap;
-          const int nblocks = (pa.n_tiles + rounds - 1) / rounds;
-          CK(cudaMemsetAsync(pa.barrier, 0, sizeof(unsigned long long), s.stream));
-          void* kargs[] = {(void*)&pa};
-          CK(cudaLaunchCooperativeKernel(tb2p_fn(), dim3(nblocks), dim3(tb2_threads), kargs, sizeof(lbm::Tb2Smem), s.stream));
-          launches++;
-          cur = (cur + n_passes) & 1;
-          passes_done += n_passes;
-        }
-      }
-      if (n_steps & 1) launch_pass(n_steps - 1, 0, false);     // the odd last step: K1a, ghost rows kept filled
     } else {
       int t = 0, p = 0;
       while (t < n_steps) {

@@ -322,65 +322,4 @@ lbm_step2_tb(const __grid_constant__ Tb2Args ta) {
   boundary_signal<float, MULTI>(a, is_boundary);
 }
 
-// ------------------------------------------------------------------------------------
-// K8  lbm_steps_tb2_persistent: ALL timestep pairs of a run in one cooperative launch, for
-// grids that live in L2 (the reference's shipped inputs).  K5 pays one grid barrier and one
-// dependent L2 round trip per TIMESTEP; here a block keeps the intermediate step in shared
-// memory and meets the others once per TWO timesteps.  Single slab (the ghost rows are the
-// slab's own); every block owns a fixed set of tiles; the buffers swap roles inside the
-// kernel.  Must be launched with cudaLaunchCooperativeKernel so that all blocks are resident.
-// ------------------------------------------------------------------------------------
-struct Tb2PersistArgs {
-  Tb2Args t;                   // geometry and constants; the per-pass pointers are set inside the kernel
-  float* lattice[2];
-  float* side[2];
-  float* window;               // own window: ghost rows at ghost_offset(pitch, parity, direction)
-  unsigned long long* av;      // 2 x n_passes steps x LBM_AV_SLOTS x LBM_AV_STRIDE words
-  unsigned long long* barrier; // zeroed before the launch
-  int first_parity;            // buffer index read by the first pass
-  int n_passes;
-  int n_tiles;
-};
-
-template <bool STRICT>
-__global__ void __launch_bounds__(LBM_TB2_THREADS, LBM_TB2_MIN_BLOCKS)
-lbm_steps_tb2_persistent(const __grid_constant__ Tb2PersistArgs pa) {
-  extern __shared__ __align__(128) unsigned char tb2_smem_raw[];
-  Tb2Smem& sm = *reinterpret_cast<Tb2Smem*>(tb2_smem_raw);
-  Tb2Args ta = pa.t;
-  StepArgs<float>& a = ta.s;
-  const int pitch = a.pitch;
-  tb2_init_smem(sm, ta.span);
-  __syncthreads();
-  uint32_t phases = 0u;
-  for (int p = 0; p < pa.n_passes; p++) {
-    const int src = (pa.first_parity + p) & 1, dst = src ^ 1;
-    a.src = pa.lattice[src];
-    a.dst = pa.lattice[dst];
-    a.side_src = pa.side[src];
-    a.side_dst = pa.side[dst];
-    a.ghost_s = pa.window + ghost_offset(pitch, src, 0);
-    a.ghost_n = pa.window + ghost_offset(pitch, src, 1);
-    a.push_up = pa.window + ghost_offset(pitch, dst, 0);
-    a.push_dn = pa.window + ghost_offset(pitch, dst, 1);
-    a.av = pa.av + (size_t)(2 * p) * (LBM_AV_STRIDE * LBM_AV_SLOTS);
-    ta.av2 = a.av + LBM_AV_STRIDE * LBM_AV_SLOTS;
-    unsigned long long q1 = 0ULL, q2 = 0ULL;
-    bool bad1 = false, bad2 = false;
-    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
-      const int seg = tile / a.tiles_x;
-      tb2_tile<STRICT>(ta, sm, tile - seg * a.tiles_x, seg, phases, q1, q2, bad1, bad2);
-    }
-    if (bad1) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
-    if (bad2) atomicOr(ta.av2 + 1, LBM_NONFINITE_MARK);
-    warp_accumulate(q1, a.av);
-    warp_accumulate(q2, ta.av2);
-    // what this block stored (generic proxy) is read by other blocks' bulk copies (async proxy)
-    // after the barrier: order the two proxies on both sides of it
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-    grid_barrier(pa.barrier, (unsigned long long)gridDim.x * (unsigned long long)(p + 1));
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-  }
-}
-
 }  // namespace lbm

@@ -81,12 +81,8 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
                                       GPU of its own; an error if two slabs share one) */
 #define LBM_GPU_KERNEL_TB2   512u  /* force the two-timesteps-per-pass kernel (temporal blocking: each
                                       distribution crosses HBM once per TWO timesteps).  The default for
-                                      fp32 grids beyond L2 with nx a multiple of 4, nx >= 512 and at least
+                                      fp32 grids beyond L2 with nx a multiple of 4, nx >= 32 and at least
                                       8 rows per GPU; an odd step of a run is done by the one-step kernel */
-#define LBM_GPU_KERNEL_TB2_PERSISTENT 2048u /* force the persistent form of the two-step kernel: all timestep
-                                      pairs of a run in one cooperative launch, one grid barrier per TWO
-                                      timesteps (single GPU, fp32, nx a multiple of 4; the default for such
-                                      grids when they live in L2) */
 #define LBM_GPU_SYNC_EVENTS 1024u  /* lbm_gpu_create with n_gpus > 1: order the slabs with CUDA events
                                       (host-recorded, no device-side waiting) even when every slab has its
                                       own GPU; always used when slabs share a GPU */

@@ -124,7 +124,7 @@ def test_kernel_selection():
     """Small single-GPU grids take the persistent kernel, big ones one launch per step,
     widths that are not a multiple of 4 the scalar kernel; all give the same bits."""
     with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA) as lat:
-        assert lat.info().kernel == L.KERNEL_TB2_PERSISTENT      # lives in L2 (tests/test_gpu_tb2.py)
+        assert lat.info().kernel == L.KERNEL_PERSISTENT          # lives in L2
     with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_CLUSTER) as lat:
         assert lat.info().kernel == L.KERNEL_CLUSTER             # opt-in: lives in one cluster's DSMEM
     with L.Lattice(130, 16, DENSITY, ACCEL, OMEGA) as lat:

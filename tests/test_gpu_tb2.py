@@ -1,6 +1,4 @@
-"""K7 and K8, the two-timesteps-per-pass kernels (temporal blocking), through the C-ABI.
-K7: one launch per pair of timesteps, any GPU count; K8: its persistent single-GPU form for
-grids that live in L2 (one grid barrier per pair of timesteps).
+"""K7, the two-timesteps-per-pass kernel (temporal blocking), through the C-ABI.
 
 Two iterations of the reference's loop (d2q9-bgk.c:180-201) fused into one pass over HBM
 must give what two separate iterations give:
@@ -33,7 +31,7 @@ def seg_rows(monkeypatch):
     return set_rows
 
 
-TWO_STEP = [L.KERNEL_TB2, L.KERNEL_TB2_PERSISTENT]
+TWO_STEP = [L.KERNEL_TB2]
 
 
 @pytest.mark.parametrize("nx,ny", [(512, 8), (520, 11), (1024, 17), (1540, 12), (2048, 70), (516, 130), (1008, 9),
@@ -49,20 +47,6 @@ def test_strict_bit_exact(nx, ny, steps, kernel):
         got = lat.download()
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), \
         "%dx%d: %d cells differ" % (nx, ny, np.count_nonzero((got != ref).any(axis=2)))
-    np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
-
-
-@pytest.mark.parametrize("rows_per_tile", [1, 2, 3, 7, 40])
-def test_persistent_form_every_tile_height(rows_per_tile, monkeypatch):
-    """K8 with more tiles than resident blocks (every block loops) and with one-row tiles."""
-    monkeypatch.setenv("LBM_TB2P_SEG_ROWS", str(rows_per_tile))
-    nx, ny, steps = 1024, 600 if rows_per_tile == 1 else 45, 7
-    cells, obst = O.random_lattice(nx, ny, seed=rows_per_tile, p_obst=0.02)
-    ref, _, av_ref_d = O.run(cells, obst, steps, D, A, W)
-    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.STRICT | L.KERNEL_TB2_PERSISTENT) as lat:
-        av = np.concatenate([lat.run(3), lat.run(steps - 3)])
-        got = lat.download()
-    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
 
 
@@ -84,7 +68,7 @@ def test_default_build_gives_the_bits_of_the_one_step_kernel(nx, ny):
     steps = 21
     cells, obst = O.random_lattice(nx, ny, seed=3, p_obst=0.02)
     res = []
-    for k in (L.KERNEL_VEC4, L.KERNEL_TB2, L.KERNEL_TB2_PERSISTENT):
+    for k in (L.KERNEL_VEC4, L.KERNEL_TB2):
         with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=k) as lat:
             av = lat.run(steps)
             res.append((lat.download(), av, lat.final_fields()))
@@ -148,17 +132,11 @@ def test_selection_and_refusals():
     with L.Lattice(4098, 4096, D, A, W) as lat:
         assert lat.info().kernel == L.KERNEL_VEC4                # the bulk copies need nx % 4 == 0
     with L.Lattice(1024, 1024, D, A, W) as lat:
-        assert lat.info().kernel == L.KERNEL_TB2_PERSISTENT      # lives in L2: one barrier per two timesteps
-    with L.Lattice(1022, 1024, D, A, W) as lat:
-        assert lat.info().kernel == L.KERNEL_PERSISTENT          # ... ragged width: one barrier per timestep
-    with L.Lattice(1024, 1024, D, A, W, f64=True) as lat:
-        assert lat.info().kernel == L.KERNEL_PERSISTENT
+        assert lat.info().kernel == L.KERNEL_PERSISTENT          # lives in L2
     with pytest.raises(L.LbmError, match="two-step kernel"):
         L.Lattice(130, 64, D, A, W, flags=L.KERNEL_TB2)
     with pytest.raises(L.LbmError, match="two-step kernel"):
         L.Lattice(512, 6, D, A, W, flags=L.KERNEL_TB2)
-    with pytest.raises(L.LbmError, match="two-step kernel"):
-        L.Lattice(512, 32, D, A, W, flags=L.KERNEL_TB2_PERSISTENT, n_gpus=2, device_ids=[0, 0])
     with pytest.raises(L.LbmError, match="two-step kernel"):
         L.Lattice(512, 20, D, A, W, flags=L.KERNEL_TB2, n_gpus=3, device_ids=[0, 0, 0])   # 6-7 rows per slab
 
@@ -174,16 +152,16 @@ def test_blown_up_lattice_reports_nan():
 
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large],
           derandomize=True)
-@given(nxq=st.integers(8, 300), ny=st.integers(8, 40), persistent=st.booleans(), steps=st.integers(1, 7), seed=st.integers(0, 10 ** 6),
+@given(nxq=st.integers(8, 300), ny=st.integers(8, 40), steps=st.integers(1, 7), seed=st.integers(0, 10 ** 6),
        p_obst=st.sampled_from([0.0, 0.02, 0.2]), slabs=st.integers(1, 3), density=st.sampled_from([0.1, 0.37]),
        accel=st.sampled_from([0.005, 0.05, 1.1]), omega=st.sampled_from([0.7, 1.0, 1.85]), split=st.integers(0, 7),
        walls=st.booleans(), seg=st.sampled_from([2, 3, 4, 9, 64]))
-def test_any_configuration_matches_the_oracle(nxq, ny, persistent, steps, seed, p_obst, slabs, density, accel, omega,
-                                              split, walls, seg):
+def test_any_configuration_matches_the_oracle(nxq, ny, steps, seed, p_obst, slabs, density, accel, omega, split,
+                                              walls, seg):
     nx = 4 * nxq
-    n = slabs if (ny // slabs >= 8 and not persistent) else 1
-    kernel = L.KERNEL_TB2_PERSISTENT if persistent else L.KERNEL_TB2
-    os.environ["LBM_TB2_SEG_ROWS"] = os.environ["LBM_TB2P_SEG_ROWS"] = str(seg)
+    n = slabs if ny // slabs >= 8 else 1
+    kernel = L.KERNEL_TB2
+    os.environ["LBM_TB2_SEG_ROWS"] = str(seg)
     try:
         cells, obst = O.random_lattice(nx, ny, seed=seed, density=density, p_obst=p_obst, walls=walls)
         ref, _, av_ref = O.run(cells, obst, steps, density, accel, omega)
@@ -194,7 +172,7 @@ def test_any_configuration_matches_the_oracle(nxq, ny, persistent, steps, seed, 
             got = lat.download()
             _, cs = lat.digest()
     finally:
-        del os.environ["LBM_TB2_SEG_ROWS"], os.environ["LBM_TB2P_SEG_ROWS"]
+        del os.environ["LBM_TB2_SEG_ROWS"]
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     assert cs == L.lattice_checksum(ref)
     ok = np.isfinite(av_ref)
