@@ -27,6 +27,7 @@ POOL = 128
 KERNEL_CLUSTER = 256
 KERNEL_TB2 = 512
 SYNC_EVENTS = 1024
+KERNEL_PAIRS = 2048
 IPC_DESC_BYTES = 256
 
 

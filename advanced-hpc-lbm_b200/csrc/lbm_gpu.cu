@@ -7,6 +7,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_cluster.cuh"
 #include "lbm_tb2.cuh"
+#include "lbm_pairs.cuh"
 
 #include <unistd.h>
 
@@ -169,6 +170,7 @@ class Grid : public GridBase {
   int cur = 0;                 // lattice buffer / window parity holding the current state (flips per pass)
   bool tb2 = false;            // two timesteps per pass (K7) wherever two steps remain
   int tb2_strips = 0, tb2_wout = 0, tb2_seg_rows = 0, tb2_span = 0, tb2_threads = 0;
+  int pairs_tile_rows = 0;     // K9: rows per block
   bool failed = false;         // a neighbour never arrived: the lattice contents are void
   unsigned long long timeout_ns = 10000000000ULL;
   long long launches = 0;
@@ -344,6 +346,7 @@ class Grid : public GridBase {
     else if (flags & LBM_GPU_KERNEL_VEC4) kernel = LBM_GPU_KERNEL_VEC4;
     else if (flags & LBM_GPU_KERNEL_PERSISTENT) kernel = LBM_GPU_KERNEL_PERSISTENT;
     else if (flags & LBM_GPU_KERNEL_TB2) kernel = LBM_GPU_KERNEL_VEC4;         // decided in choose_tb2()
+    else if (flags & LBM_GPU_KERNEL_PAIRS) kernel = LBM_GPU_KERNEL_VEC4;       // decided in choose_pairs()
     else if (flags & LBM_GPU_KERNEL_CLUSTER) kernel = LBM_GPU_KERNEL_VEC4;     // decided in choose_kernel()
     else kernel = LBM_GPU_KERNEL_VEC4;                         // refined in choose_kernel()
     if (flags & LBM_GPU_KERNEL_TMA) {
@@ -424,7 +427,8 @@ class Grid : public GridBase {
 
   void choose_kernel() {
     const bool forced = flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT |
-                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER | LBM_GPU_KERNEL_TB2);
+                                 LBM_GPU_KERNEL_TMA | LBM_GPU_KERNEL_CLUSTER | LBM_GPU_KERNEL_TB2 |
+                                 LBM_GPU_KERNEL_PAIRS);
     // K6 is opt-in only: 16 SMs doing all the arithmetic are no faster than K5 spreading it
     // over the whole chip (profiles/r01_small_grids.md).
     if (flags & LBM_GPU_KERNEL_CLUSTER) {
@@ -469,7 +473,7 @@ class Grid : public GridBase {
   bool tb2_possible(int rows_min) const {
     if (sizeof(real) != 4) return false;
     if (flags & (LBM_GPU_KERNEL_SCALAR | LBM_GPU_KERNEL_VEC4 | LBM_GPU_KERNEL_PERSISTENT | LBM_GPU_KERNEL_TMA |
-                 LBM_GPU_KERNEL_CLUSTER)) return false;
+                 LBM_GPU_KERNEL_CLUSTER | LBM_GPU_KERNEL_PAIRS)) return false;
     if (getenv("LBM_GPU_NO_TB2") && getenv("LBM_GPU_NO_TB2")[0] == '1') return false;
     return (prm.nx % 4 == 0) && prm.nx >= 32 && rows_min >= kTb2MinRows;
   }
@@ -516,6 +520,45 @@ class Grid : public GridBase {
       if (nsegs == 1 || rows - (nsegs - 1) * seg_rows >= 2) return;
       nsegs--;
     }
+  }
+
+  // K9 (two timesteps per grid barrier) for the small grids the persistent kernel K5 would
+  // take: single GPU, fp32, nx a multiple of 4 and at most 256, every block resident.
+  const void* pairs_fn() const {
+    if constexpr (sizeof(real) == 4)
+      return (flags & LBM_GPU_STRICT) ? (const void*)lbm::lbm_steps_pairs<true> : (const void*)lbm::lbm_steps_pairs<false>;
+    return nullptr;
+  }
+  dim3 pairs_block() const { return dim3((unsigned)round_up(prm.nx / 4, 32), (unsigned)(pairs_tile_rows + 2)); }
+  size_t pairs_smem() const { return (size_t)(pairs_tile_rows + 2) * 9 * prm.nx * sizeof(float); }
+
+  void choose_pairs() {
+    const bool want = (flags & LBM_GPU_KERNEL_PAIRS) != 0;
+    const bool small = (kernel == LBM_GPU_KERNEL_PERSISTENT) && !(flags & LBM_GPU_KERNEL_PERSISTENT);
+    static const bool off = getenv("LBM_GPU_NO_PAIRS") && getenv("LBM_GPU_NO_PAIRS")[0] == '1';
+    if (!want && (!small || off)) return;
+    bool ok = sizeof(real) == 4 && slabs.size() == 1 && !slab_mode && prm.nx % 4 == 0 && prm.nx >= 4 &&
+              prm.nx <= LBM_PAIRS_MAX_NX && slabs[0].rows >= 4;
+    if (ok) {
+      Slab<real>& s = slabs[0];
+      CK(cudaSetDevice(s.device));
+      int sms = 0, coop = 0, per_sm = 0;
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+      CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
+      // one block per SM if the grid allows it: the fewest rows per block that still fits
+      pairs_tile_rows = std::min(LBM_PAIRS_MAX_TILE_ROWS, std::max(1, (s.rows + sms - 1) / sms));
+      if (const char* e = getenv("LBM_PAIRS_TILE_ROWS"))                      // tuning knob
+        pairs_tile_rows = std::min(LBM_PAIRS_MAX_TILE_ROWS, std::max(1, atoi(e)));
+      pairs_tile_rows = std::min(pairs_tile_rows, s.rows - 2);
+      const dim3 b = pairs_block();
+      ok = coop && cudaFuncSetAttribute(pairs_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairs_smem()) == cudaSuccess &&
+           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_fn(), (int)(b.x * b.y), pairs_smem()) == cudaSuccess &&
+           (long long)per_sm * sms >= (s.rows + pairs_tile_rows - 1) / pairs_tile_rows;
+      cudaGetLastError();
+    }
+    if (ok) kernel = LBM_GPU_KERNEL_PAIRS;
+    else if (want) throw CudaError{"the pairs kernel needs a single-GPU fp32 lattice with nx a multiple of 4 and <= 256 whose "
+                                   "blocks are all resident"};
   }
 
   // single-process form: decide once all slabs exist
@@ -912,6 +955,32 @@ class Grid : public GridBase {
       CK(cudaLaunchCooperativeKernel(persistent_fn(), dim3(nblocks), dim3(bx, by), kargs, 0, s.stream));
       launches++;
       cur = (cur + n_steps) & 1;
+    } else if (kernel == LBM_GPU_KERNEL_PAIRS) {
+      const int n_pairs = n_steps / 2;
+      if constexpr (sizeof(real) == 4) {
+        if (n_pairs > 0) {
+          Slab<real>& s = slabs[0];
+          CK(cudaSetDevice(s.device));
+          lbm::PairsArgs pa;
+          memset(&pa, 0, sizeof pa);
+          fill_step_args(pa.s, s, 0);
+          for (int b = 0; b < 2; b++) { pa.lattice[b] = s.lattice[b]; pa.side[b] = s.side[b]; }
+          pa.window = (real*)s.win;
+          pa.av = s.av;
+          pa.barrier = s.sync + kGridBarrier;
+          pa.first_parity = cur;
+          pa.n_pairs = n_pairs;
+          pa.tile_rows = pairs_tile_rows;
+          CK(cudaMemsetAsync(pa.barrier, 0, sizeof(unsigned long long), s.stream));
+          void* kargs[] = {(void*)&pa};
+          CK(cudaLaunchCooperativeKernel(pairs_fn(), dim3((unsigned)((s.rows + pairs_tile_rows - 1) / pairs_tile_rows)),
+                                         pairs_block(), kargs, pairs_smem(), s.stream));
+          launches++;
+          cur = (cur + n_pairs) & 1;
+          passes_done += n_pairs;
+        }
+      }
+      if (n_steps & 1) launch_pass(n_steps - 1, 0, false);     // the odd last step: K1a
     } else {
       int t = 0, p = 0;
       while (t < n_steps) {
@@ -1175,6 +1244,7 @@ int create_impl(const typename ParamT<real>::type* params, const real* cells_aos
     }
     g->connect_local();
     g->choose_kernel();
+    g->choose_pairs();
     g->choose_tb2();
     g->prepare();
   } catch (const CudaError& e) {

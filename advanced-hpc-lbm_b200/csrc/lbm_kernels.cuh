@@ -646,9 +646,14 @@ __device__ __forceinline__ void boundary_signal(const StepArgs<real>& a, const b
     __threadfence_system();            // this thread's ghost-row pushes are visible system-wide
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
+      // the last edge block of this pass publishes it.  The counter restarts from zero for the
+      // next pass, whose kernel may have another number of edge blocks (K7 and K1a alternate);
+      // that kernel's blocks count only after this grid has completed (stream order, or
+      // cudaGridDependencySynchronize under programmatic launch).
       const unsigned long long nb = edge_tile_count(a.tiles_x, a.tiles_y, a.edge_tiles);
       const unsigned long long old = atomicAdd(a.boundary_done, 1ULL);
-      if (old + 1ULL == nb * (a.pass + 1ULL)) {
+      if (old + 1ULL == nb) {
+        atomicExch(a.boundary_done, 0ULL);
         __threadfence_system();
         st_release_sys(a.up_flag, a.pass + 1ULL);
         st_release_sys(a.dn_flag, a.pass + 1ULL);
@@ -672,25 +677,21 @@ __global__ void lbm_wait_neighbours(const StepArgs<real> a) {
 // that element with a scalar load that also implements the periodic wrap in x.
 // blockDim = (BX, BY), BX a multiple of 32 so that a warp never spans two rows.
 // ------------------------------------------------------------------------------------
-template <typename real, bool STRICT, bool CG>
-__device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a, const QuadConsts<real, STRICT>& qc,
-                                                        const int tx, const int ty) {
-  const int x0 = (tx * (int)blockDim.x + (int)threadIdx.x) * 4;
-  const int r = ty * (int)blockDim.y + (int)threadIdx.y;        // local row
-  const bool active = (x0 < a.nx) && (r < a.rows);
+// The pull of one quad (d2q9-bgk.c:990-998 for four neighbouring cells): cells xc..xc+3 of
+// local row rc, nine aligned 128-bit loads plus the two x-shift elements from the
+// neighbouring lanes.  Every thread of the warp must call it (shuffles); `mbits` are the
+// quad's mask bits, `obits` those plus the padding cells of a ragged width.
+template <typename real, bool CG>
+__device__ __forceinline__ void vec4_pull(const StepArgs<real>& a, const int rc, const int xc, real (&in)[4][9],
+                                          uint32_t& mbits, uint32_t& obits) {
   const int lane = threadIdx.x & 31;
-
-  // clamp so that inactive threads still form valid addresses (they take part in the
-  // shuffles but never store)
-  const int xc = active ? x0 : 0;
-  const int rc = active ? r : 0;
   const long long PS = a.plane_stride;
   const long long oC = (long long)rc * a.pitch;
 
-  // Row sources.  South/north neighbours of the slab's first/last row live in the halo
-  // window; planes 1,3 of the centre row / 5,6 of the south row / 7,8 of the north row
-  // come from the accelerated side row when that row is global row ny-2 (the window
-  // already holds accelerated values).  All of this is warp-uniform, and all but five
+  // Row sources.  South/north neighbours of the slab's first/last row live in the ghost
+  // rows; planes 1,3 of the centre row / 5,6 of the south row / 7,8 of the north row
+  // come from the accelerated side row when that row is global row ny-2 (the ghost rows
+  // already hold accelerated values).  All of this is warp-uniform, and all but five
   // rows of a slab take the first branch.
   const bool first = (rc == 0), last = (rc == a.rows - 1);
   const bool cA = (rc == a.accel_row), sA = (rc - 1 == a.accel_row), nA = (rc + 1 == a.accel_row);
@@ -724,7 +725,7 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
                    v3 = load4<real, CG>(p3 + xc), v4 = load4<real, CG>(p4 + xc), v5 = load4<real, CG>(p5 + xc),
                    v6 = load4<real, CG>(p6 + xc), v7 = load4<real, CG>(p7 + xc), v8 = load4<real, CG>(p8 + xc);
   const uint32_t mword = a.mask[(long long)rc * a.mask_pitch + (xc >> 5)];
-  const uint32_t mbits = (mword >> (xc & 31)) & 0xFu;
+  mbits = (mword >> (xc & 31)) & 0xFu;
 
   // element x0-1 of planes 1,5,8 and x0+4 of planes 3,6,7 from the neighbouring lanes
   real l1 = __shfl_up_sync(0xffffffffu, v1.w, 1), l5 = __shfl_up_sync(0xffffffffu, v5.w, 1),
@@ -740,9 +741,8 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
   // padding cells are treated as obstacles so that they add nothing to the average.
   const int nvalid = a.nx - xc;
   const bool n1 = (nvalid == 1), n2 = (nvalid == 2), n3 = (nvalid == 3);
-  const uint32_t obits = (nvalid < 4) ? (mbits | ((0xFu << nvalid) & 0xFu)) : mbits;
+  obits = (nvalid < 4) ? (mbits | ((0xFu << nvalid) & 0xFu)) : mbits;
 
-  real in[4][9], out[4][9];
   in[0][0] = v0.x; in[1][0] = v0.y; in[2][0] = v0.z; in[3][0] = v0.w;
   in[0][1] = l1;   in[1][1] = v1.x; in[2][1] = v1.y; in[3][1] = v1.z;
   in[0][2] = v2.x; in[1][2] = v2.y; in[2][2] = v2.z; in[3][2] = v2.w;
@@ -752,6 +752,26 @@ __device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a,
   in[0][6] = n1 ? r6 : v6.y; in[1][6] = n2 ? r6 : v6.z; in[2][6] = n3 ? r6 : v6.w; in[3][6] = r6;
   in[0][7] = n1 ? r7 : v7.y; in[1][7] = n2 ? r7 : v7.z; in[2][7] = n3 ? r7 : v7.w; in[3][7] = r7;
   in[0][8] = l8;   in[1][8] = v8.x; in[2][8] = v8.y; in[3][8] = v8.z;
+}
+
+template <typename real, bool STRICT, bool CG>
+__device__ __forceinline__ unsigned long long vec4_tile(const StepArgs<real>& a, const QuadConsts<real, STRICT>& qc,
+                                                        const int tx, const int ty) {
+  const int x0 = (tx * (int)blockDim.x + (int)threadIdx.x) * 4;
+  const int r = ty * (int)blockDim.y + (int)threadIdx.y;        // local row
+  const bool active = (x0 < a.nx) && (r < a.rows);
+
+  // clamp so that inactive threads still form valid addresses (they take part in the
+  // shuffles but never store)
+  const int xc = active ? x0 : 0;
+  const int rc = active ? r : 0;
+  const long long PS = a.plane_stride;
+  const long long oC = (long long)rc * a.pitch;
+  const bool first = (rc == 0), last = (rc == a.rows - 1), cA = (rc == a.accel_row);
+
+  real in[4][9], out[4][9];
+  uint32_t mbits, obits;
+  vec4_pull<real, CG>(a, rc, xc, in, mbits, obits);
 
   bool bad;
   unsigned long long q = quad_update<real, STRICT>(in, obits, qc, out, bad);

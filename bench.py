@@ -326,7 +326,7 @@ def bind_near_gpu(local_rank):
 
 
 KERNEL_NAMES = {4: "lbm_step_scalar", 16: "lbm_step_vec4", 64: "lbm_steps_persistent", 8: "lbm_step_tma",
-                256: "lbm_steps_cluster", 512: "lbm_step2_tb (two timesteps per pass) + lbm_step_vec4 for an odd step"}
+                256: "lbm_steps_cluster", 2048: "lbm_steps_pairs (two timesteps per grid barrier)", 512: "lbm_step2_tb (two timesteps per pass) + lbm_step_vec4 for an odd step"}
 
 
 def connect(lat, L, slabs, R):

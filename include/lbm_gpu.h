@@ -83,6 +83,9 @@ typedef struct lbm_gpu lbm_gpu;   /* opaque handle: one lattice on one or more G
                                       distribution crosses HBM once per TWO timesteps).  The default for
                                       fp32 grids beyond L2 with nx a multiple of 4, nx >= 32 and at least
                                       8 rows per GPU; an odd step of a run is done by the one-step kernel */
+#define LBM_GPU_KERNEL_PAIRS 2048u  /* force the small-grid persistent kernel that meets at a grid barrier once
+                                      per TWO timesteps (single GPU, fp32, nx a multiple of 4 and <= 256); the
+                                      default for such grids */
 #define LBM_GPU_SYNC_EVENTS 1024u  /* lbm_gpu_create with n_gpus > 1: order the slabs with CUDA events
                                       (host-recorded, no device-side waiting) even when every slab has its
                                       own GPU; always used when slabs share a GPU */

@@ -124,6 +124,8 @@ def test_kernel_selection():
     """Small single-GPU grids take the persistent kernel, big ones one launch per step,
     widths that are not a multiple of 4 the scalar kernel; all give the same bits."""
     with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA) as lat:
+        assert lat.info().kernel == L.KERNEL_PAIRS               # lives in L2, two timesteps per barrier (test_gpu_pairs.py)
+    with L.Lattice(640, 512, DENSITY, ACCEL, OMEGA) as lat:
         assert lat.info().kernel == L.KERNEL_PERSISTENT          # lives in L2
     with L.Lattice(128, 128, DENSITY, ACCEL, OMEGA, flags=L.KERNEL_CLUSTER) as lat:
         assert lat.info().kernel == L.KERNEL_CLUSTER             # opt-in: lives in one cluster's DSMEM
