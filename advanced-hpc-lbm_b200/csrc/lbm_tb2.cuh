@@ -272,7 +272,9 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
     }
     mbits_prev = mbits;
     mbits = mbits_next;
+#if !(defined(LBM_EXPERIMENTS) && defined(LBM_TB2_EXPERIMENT_NO_SECOND_BARRIER))   // timing experiment only: WRONG results
     __syncthreads();          // the ring rows read above are overwritten by the next iteration
+#endif
   }
 
 }

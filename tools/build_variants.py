@@ -17,6 +17,7 @@ VARIANTS = {
     "scalar": ["-DLBM_PACKED=0"],
     "scalar_mb5": ["-DLBM_PACKED=0", "-DLBM_MIN_BLOCKS=5", "-DLBM_PERSIST_MIN_BLOCKS=4"],
     "tb2_mb2": ["-DLBM_TB2_MIN_BLOCKS=2"],
+    "tb2_x_nobarrier": ["-DLBM_EXPERIMENTS", "-DLBM_TB2_EXPERIMENT_NO_SECOND_BARRIER"],   # wrong results, timing only
 }
 if os.environ.get("LBM_VARIANTS"):
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ["LBM_VARIANTS"].split(",")}
