@@ -496,14 +496,22 @@ class Grid : public GridBase {
         tb2_span = LBM_TB2_SPAN;
       }
       tb2_threads = (int)round_up(tb2_span / 4, 32);
-      // Segment height: every segment recomputes two rows of the first sub-step, so tall is
-      // cheap (64 rows: 3 %), but a grid should still be cut into at least ~6 waves of
-      // resident blocks or the last wave leaves SMs idle (4096^2: 64 rows = 1.3 waves).
+      // Segment height.  Every segment recomputes two rows of the first sub-step, so tall is
+      // cheap; but the blocks of a launch run in "waves" of the resident blocks and a last wave
+      // that is nearly empty leaves the SMs idle (16384 rows in 64-row segments: 19.03 waves).
+      // Score each height by (rows / (rows + 2)) x (waves / ceil(waves)) and take the best; grids
+      // with few blocks prefer short segments so that there are several waves at all.
       int sms = 148, rows_max = 0;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, slabs[0].device);
       for (auto& s : slabs) rows_max = std::max(rows_max, s.rows);
-      const long long want_segs = (6LL * LBM_TB2_MIN_BLOCKS * sms + tb2_strips - 1) / tb2_strips;
-      tb2_seg_rows = (int)std::min<long long>(64, std::max<long long>(16, rows_max / std::max<long long>(1, want_segs)));
+      const double resident = (double)LBM_TB2_MIN_BLOCKS * sms;
+      double best = -1.0;
+      tb2_seg_rows = 64;
+      for (int h = 16; h <= 128; h++) {
+        const double waves = (double)tb2_strips * ((rows_max + h - 1) / h) / resident;
+        const double score = (double)h / (h + 2) * waves / std::ceil(waves) * (waves >= 4.0 ? 1.0 : 0.25 * waves);
+        if (score > best + 1e-9) { best = score; tb2_seg_rows = h; }
+      }
       if (const char* e = getenv("LBM_TB2_SEG_ROWS")) tb2_seg_rows = std::max(2, atoi(e));   // tuning knob
       tb2 = true;
       kernel = LBM_GPU_KERNEL_TB2;

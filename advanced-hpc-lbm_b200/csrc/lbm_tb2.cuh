@@ -50,7 +50,8 @@ struct Tb2Smem {
   float r013[2][3][LBM_TB2_ROWF];    // sub-step-1 rows: planes 0,1,3 (read one iteration later)
   float r256[3][3][LBM_TB2_ROWF];    // planes 2,5,6 (read two iterations later)
   float r78[2][LBM_TB2_ROWF];        // planes 7,8 (read in the same iteration; plane 4 stays in registers)
-  unsigned long long mbar[2];
+  unsigned long long mbar[2];         // "stage filled" (transaction barriers of the bulk copies)
+  unsigned long long mbar_free;       // "ring slots of the previous iteration have been read" (one arrival per warp)
 };
 static_assert(sizeof(Tb2Smem) <= 75 * 1024, "three blocks per SM need <= 75 KB each");
 static_assert((LBM_TB2_ROWF * sizeof(float)) % 16 == 0, "staged rows must keep 16-byte alignment");
@@ -89,30 +90,34 @@ __device__ __forceinline__ const float* tb2_row_ptr(const StepArgs<float>& a, co
   return a.src + (long long)k * a.plane_stride + (long long)row * a.pitch;
 }
 
-// warp 0: start the copies of the nine plane-rows that sub-step 1 on row r pulls from -- lane
-// 0 announces the bytes, lanes 0..8 each work out where "their" plane-row lives and copy it,
-// in as many pieces as the periodic wrap in x cuts the span into (up to three when the span
-// is the whole width plus halo)
+// Start the copies of the nine plane-rows that sub-step 1 on row r pulls from.  The work is
+// spread over the block so that no warp lags behind the others: thread t < 9 (one per plane,
+// in different warps first) works out where "its" plane-row lives and copies it, in as many
+// pieces as the periodic wrap in x cuts the span into (up to three when the span is the
+// whole width plus halo).  The bytes were announced before by tb2_expect.
+__device__ __forceinline__ void tb2_expect(Tb2Smem& sm, const int stage, const int span) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.mbar[stage])),
+               "r"((uint32_t)(9 * span * sizeof(float))) : "memory");
+}
+__device__ __forceinline__ int tb2_plane_of_thread() {
+  const int nwarps = (int)blockDim.x >> 5, w = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  const int k = w + nwarps * lane;
+  return (k < 9) ? k : -1;
+}
 __device__ __forceinline__ void tb2_issue(const StepArgs<float>& a, Tb2Smem& sm, const int stage, const int r,
-                                          const int s0, const int span, const int lane) {
+                                          const int s0, const int span, const int k) {
+  if (k < 0) return;
   unsigned long long* bar = &sm.mbar[stage];
-  if (lane == 0)
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"((uint32_t)(9 * span * sizeof(float))) : "memory");
-  __syncwarp();
-  if (lane < 9) {
-    const int k = lane;
-    const int dy = (k == 2 || k == 5 || k == 6) ? -1 : (k == 4 || k == 7 || k == 8) ? 1 : 0;
-    const float* row = tb2_row_ptr(a, k, r + dy);
-    float* dst = &sm.in[stage][k][LBM_TB2_PAD];
-    int col = s0, left = span;
-    while (left > 0) {
-      const int n = min(left, a.nx - col);
-      tb2_bulk_load(dst, row + col, (uint32_t)n * 4u, bar);
-      dst += n;
-      left -= n;
-      col = 0;
-    }
+  const int dy = (k == 2 || k == 5 || k == 6) ? -1 : (k == 4 || k == 7 || k == 8) ? 1 : 0;
+  const float* row = tb2_row_ptr(a, k, r + dy);
+  float* dst = &sm.in[stage][k][LBM_TB2_PAD];
+  int col = s0, left = span;
+  while (left > 0) {
+    const int n = min(left, a.nx - col);
+    tb2_bulk_load(dst, row + col, (uint32_t)n * 4u, bar);
+    dst += n;
+    left -= n;
+    col = 0;
   }
 }
 
@@ -128,6 +133,13 @@ __device__ __forceinline__ void tb2_get_west(const float* row, const int c0, flo
 __device__ __forceinline__ void tb2_get_east(const float* row, const int c0, float& v0, float& v1, float& v2, float& v3) {
   const float4 v = *reinterpret_cast<const float4*>(row + LBM_TB2_PAD + c0);
   v0 = v.y; v1 = v.z; v2 = v.w; v3 = row[LBM_TB2_PAD + c0 + 4];
+}
+// this warp has finished reading the ring slots of the current iteration (release: the reads
+// above are performed before any thread that waits on the barrier overwrites the slots)
+__device__ __forceinline__ void tb2_ring_read_done(Tb2Smem& sm) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.mbar_free)) : "memory");
 }
 __device__ __forceinline__ void tb2_put(float* row, const int c0, const float (&o)[4][9], const int k) {
   *reinterpret_cast<float4*>(row + LBM_TB2_PAD + c0) = make_float4(o[0][k], o[1][k], o[2][k], o[3][k]);
@@ -154,10 +166,10 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
   const bool owned = (tid >= 1) && (4 * tid < ta.span) && (c0 - LBM_TB2_PAD < ta.wout) &&
                      (X0 + c0 - LBM_TB2_PAD < a.nx);
 
-  if (tid < 32) {
+  const int my_plane = tb2_plane_of_thread();
+  if (tid == 0) { tb2_expect(sm, 0, ta.span); tb2_expect(sm, 1, ta.span); }
 #pragma unroll 1
-    for (int k = 0; k < 2; k++) tb2_issue(a, sm, k, R0 - 1 + k, S0, ta.span, tid);
-  }
+  for (int k = 0; k < 2; k++) tb2_issue(a, sm, k, R0 - 1 + k, S0, ta.span, my_plane);
 
   const QuadConsts<float, STRICT> qc(a.omega);
   const int mword_idx = xg >> 5, mshift = xg & 31;
@@ -179,6 +191,7 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
       // ---------------- sub-step 1 on row r: pulled values are staged in sm.in[st] ----------
       tb2_mbar_wait(&sm.mbar[st], (phases >> st) & 1u);
       phases ^= 1u << st;
+      if (tid == 0 && i + 2 < n_it) tb2_expect(sm, st, ta.span);      // the refill of this stage, issued after the barrier below
       float in[4][9], out[4][9];
       const float(*row)[LBM_TB2_ROWF] = sm.in[st];
       tb2_get(row[0], c0, in[0][0], in[1][0], in[2][0], in[3][0]);
@@ -199,6 +212,13 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
           cell_accelerate<float, STRICT>(out[j][1], out[j][3], out[j][5], out[j][6], out[j][7], out[j][8],
                                          (mbits >> j) & 1u, a.aw1, a.aw2);
       }
+      // the ring slots written now were read by sub-step 2 of the previous iteration: every warp
+      // has said so (mbar_free) a whole sub-step ago, so this wait is normally free -- it replaces
+      // a second block barrier per row, which cost 11 % (profiles/r02_kernel_variants.md)
+      if (i > 0) {
+        tb2_mbar_wait(&sm.mbar_free, (phases >> 2) & 1u);
+        phases ^= 4u;
+      }
       tb2_put(sm.r013[i & 1][0], c0, out, 0);
       tb2_put(sm.r013[i & 1][1], c0, out, 1);
       tb2_put(sm.r013[i & 1][2], c0, out, 3);
@@ -211,7 +231,7 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
       for (int j = 0; j < 4; j++) keep4[j] = out[j][4];
     }
     __syncthreads();          // ring rows of this iteration are complete; stage `st` has been read by everyone
-    if (tid < 32 && i + 2 < n_it) tb2_issue(a, sm, st, r + 2, S0, ta.span, tid);
+    if (i + 2 < n_it) tb2_issue(a, sm, st, r + 2, S0, ta.span, my_plane);
 
     if (i >= 2) {
       // ---------------- sub-step 2 on row y = r - 1, pulling sub-step-1 rows y-1, y, y+1 ----
@@ -229,6 +249,7 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
       for (int j = 0; j < 4; j++) in[j][4] = keep4[j];         // row y + 1 = r, this thread's own cells
       tb2_get_east(sm.r78[0], c0, in[0][7], in[1][7], in[2][7], in[3][7]);
       tb2_get_west(sm.r78[1], c0, in[0][8], in[1][8], in[2][8], in[3][8]);
+      tb2_ring_read_done(sm);
       bool bad;
       const unsigned long long q = quad_update<float, STRICT>(in, mbits_prev, qc, out, bad);
       if (owned) {
@@ -270,11 +291,11 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
         }
       }
     }
+    else {
+      tb2_ring_read_done(sm);   // nothing read in the first two iterations: keep one arrival per warp per iteration
+    }
     mbits_prev = mbits;
     mbits = mbits_next;
-#if !(defined(LBM_EXPERIMENTS) && defined(LBM_TB2_EXPERIMENT_NO_SECOND_BARRIER))   // timing experiment only: WRONG results
-    __syncthreads();          // the ring rows read above are overwritten by the next iteration
-#endif
   }
 
 }
@@ -292,6 +313,7 @@ __device__ __forceinline__ void tb2_init_smem(Tb2Smem& sm, const int span) {
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[0])) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[1])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sm.mbar_free)), "r"((uint32_t)(blockDim.x >> 5)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 }

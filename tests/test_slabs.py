@@ -68,6 +68,28 @@ WORKER = textwrap.dedent("""
     av = slabs.combine_step_sums(local, free, dist, world)
     want = (np.arange(steps) * world + 10.0 * sum(range(world))) / sum(100 + r for r in range(world))
     assert np.allclose(av, want, rtol=0, atol=1e-15), (av, want)
+    # 3. all descriptors to every rank, in rank order (what lbm_gpu_ipc_connect_all takes)
+    all_descs = slabs.gather_descriptors(desc, world, dist)
+    assert all_descs.shape == (world, 256) and [int(d[0]) for d in all_descs] == [r + 1 for r in range(world)]
+    # 4. bench.py's reductions over ranks: wrapping 64-bit checksum sum, doubles, all_true
+    sys.path.insert(0, %(root)r)
+    import bench
+    R = bench.Ranks.__new__(bench.Ranks)
+    R.rank, R.local_rank, R.world, R.dist = rank, rank, world, dist
+    bench._f64 = lambda: __import__("torch").float64
+    orig = bench.Ranks._reduce
+    def cpu_reduce(self, values, op, dtype):
+        import torch
+        t = torch.tensor(list(values), dtype=dtype)
+        dist.all_reduce(t, op=op)
+        return t.tolist()
+    bench.Ranks._reduce = cpu_reduce
+    x = (0xF123456789ABCDEF + rank * 0x8000000000000001) & (2 ** 64 - 1)
+    want64 = sum((0xF123456789ABCDEF + r * 0x8000000000000001) for r in range(world)) & (2 ** 64 - 1)
+    assert R.sum_u64(x) == want64
+    assert R.sum(1.5 + rank) == sum(1.5 + r for r in range(world)) and R.max(float(rank)) == world - 1
+    assert np.array_equal(R.sum_array([1.0, rank]), [world, sum(range(world))])
+    assert R.all_true(True) and not R.all_true(rank != 1)
     dist.barrier()
     if rank == 0:
         print("OK")
