@@ -82,7 +82,7 @@ struct IpcDesc {
   long long local_free_cells;
   int32_t cur;                        // lattice buffer holding the current state
   int32_t tb2_ok;                     // this slab could run the two-step kernel
-  cudaIpcMemHandle_t handle;          // of the halo window (the lattice itself is never shared)
+  cudaIpcMemHandle_t handle;          // of the window (the lattice itself is never shared)
   char gpu_uuid[16];                  // physical GPU: two flag-ordered slabs must not share one
 };
 static_assert(sizeof(IpcDesc) <= LBM_GPU_IPC_DESC_BYTES, "descriptor too large");
@@ -112,7 +112,7 @@ struct Slab {
   real* lattice[2] = {nullptr, nullptr};
   real* side[2] = {nullptr, nullptr};
   uint32_t* mask = nullptr;
-  // halo window: [parity 2][direction 2][3 planes][pitch] reals, then the sync words.
+  // window: ghost rows [parity 2][direction 2][depth 2][9 planes][pitch], ghost mask rows, sync words.
   // The only memory neighbours (other GPUs / processes) read or write.
   char* win = nullptr;
   size_t win_bytes = 0, off_sync = 0, off_gmask = 0;
@@ -209,7 +209,7 @@ class Grid : public GridBase {
   // the pages instead of paying cudaFree + cudaMalloc of ~20 GB each time (25-80 ms).
   // Not the default: the pool's first growth is slower than one cudaMalloc (0.4 s for
   // 19 GB), which a one-shot CLI run would pay for nothing, and the memory stays with the
-  // process after lbm_gpu_destroy.  The halo window is always a plain allocation (CUDA IPC).
+  // process after lbm_gpu_destroy.  The window is always a plain allocation (CUDA IPC).
   bool use_pool() const { return (flags & LBM_GPU_POOL) != 0; }
   void pool_alloc(void** p, size_t bytes, Slab<real>& s) {
     if (use_pool()) {
@@ -232,7 +232,7 @@ class Grid : public GridBase {
     if (s.pooled) cudaFreeAsync(p, s.stream);
     else cudaFree(p);
   }
-  // The halo window must be a plain cudaMalloc allocation (CUDA IPC), and a plain cudaFree
+  // The window must be a plain cudaMalloc allocation (CUDA IPC), and a plain cudaFree
   // is a device-wide synchronisation that was measured to take up to 0.6 s when it follows
   // large transfers.  With LBM_GPU_POOL a destroyed lattice parks its window in a small
   // per-process cache instead and the next lattice of the same width picks it up.

@@ -3,7 +3,7 @@
 // One fused kernel per timestep does what the reference's timestep_new2 does
 // (d2q9-bgk.c:228-1813): accelerate_flow (:229-260), pull-propagate (:990-998),
 // rebound (:971-981), BGK collision (:983-1100) and the av_velocity contribution
-// (:1103-1130), plus -- new here -- the halo push into the neighbouring slabs.
+// (:1103-1130), plus -- new here -- the ghost-row push into the neighbouring slabs.
 //
 // Data layout in HBM (one "slab" = the rows one GPU holds):
 //   lattice  2 buffers x 9 planes x rows x pitch   structure-of-arrays;
@@ -847,7 +847,7 @@ lbm_step_vec4(const __grid_constant__ StepArgs<real> a) {
 // (tools/probe/tma_probe.cu) -- so the x-shifted planes get a 4-element halo box on the
 // side they pull from and the threads read that one extra element from shared memory,
 // where K1a uses a warp shuffle.  The two ends of a row (periodic wrap in x) and the few
-// rows that read the halo window or the accelerated side row keep the direct-load path
+// rows that read the ghost rows or the accelerated side row keep the direct-load path
 // (vec4_tile), chosen per block.  Built to measure whether staging buys anything over
 // K1a: it does not (profiles/r01_kernel_variants.md), every byte is used once either way.
 // ------------------------------------------------------------------------------------
@@ -1060,7 +1060,7 @@ lbm_step_scalar(const __grid_constant__ StepArgs<real> a) {
 // There the per-step cost of K1a is launch latency, not bandwidth.  Every block owns a
 // fixed set of tiles, loops over the steps, and meets the other blocks at a grid barrier
 // (one atomic per block) between steps; buffers swap roles inside the kernel.  Single
-// slab only (the halo window is the slab's own).  Loads are L2-only (see ld4cg).
+// slab only (the ghost rows are the slab's own).  Loads are L2-only (see ld4cg).
 // VEC = 4 cells per thread (K1a's tile) or, for the smallest grids, 1 cell per thread
 // (K1b's tile): four times as many threads share the step's dependent-latency chain.
 // Must be launched with cudaLaunchCooperativeKernel so that all blocks are resident.

@@ -25,6 +25,22 @@ so nothing stays cached between timesteps or steps.
   --impl reference   the reference's own timestep_new2, compiled from /root/reference
           into oracle/_ref (or the oracle port if that is absent), on the host cores
           with all threads, on a bounded sample of the same workload.
+
+Also in the JSON line (round 2):
+  parity    run BEFORE the timed region: the kernels of the headline path (K1a and the
+            two-timestep K7, MULTI=true instantiations when N > 1, through create_slab /
+            IPC / connect_all / run_sums) against the CPU oracle's exact lattice checksum and
+            av_vels (strict build) and against a one-slab GPU run (default build); at N > 1
+            also the protocol-exit test (a rank asked for fewer steps makes the others return
+            an error within the time-out); total-mass drift of the full grid over the timed
+            timesteps.  A mismatch makes the process exit non-zero.
+  strong    N > 1: the single 16384 x 16384 grid split over the N GPUs (configs[3]),
+            2 x T timesteps, device-timed, max over ranks.
+  shipped   N = 1: the reference's four shipped inputs, full step counts: MLUPS, kernel
+            chosen, check.py's criterion against the golden files.
+  roofline  of the dominant kernel; K7 advances TWO timesteps per launch with the 72 B per
+            cell of one pass, so algorithmic bytes per update = 36; `traffic` is the ncu
+            figure of the committed capture named in `traffic_source`.
 """
 import argparse
 import ctypes
@@ -535,7 +551,7 @@ def main():
             host_memory = "pageable"
             return _Pageable(shape, dtype)
 
-    def make_lattice(ny, row0, nrows, obstacles, global_free, bits=False):
+    def make_lattice(ny, row0, nrows, obstacles, bits=False):
         # LBM_GPU_POOL: device memory of a destroyed lattice is reused by the next create
         if world == 1:
             return L.Lattice(NX, ny, DENSITY, ACCEL, OMEGA, obstacles=obstacles, bits=bits, flags=L.POOL)
@@ -562,9 +578,8 @@ def main():
     # this rank's rows of the obstacle mask, as the reference holds it: one int per cell
     pin_obst = host_array((nrows, NX), np.int32)
     pin_obst.array[...] = channel_mask(NX, ny, rows=(row0, row0 + nrows))
-    global_free = sum_over_ranks(float((pin_obst.array == 0).sum()))
 
-    lat = make_lattice(ny, row0, nrows, pin_obst.array, global_free)
+    lat = make_lattice(ny, row0, nrows, pin_obst.array)
     for _ in range(W):
         lat.run_timed(T)
     mass0 = sum_over_ranks(lat.digest()[0])
@@ -610,7 +625,7 @@ def main():
             sny = ROWS_PER_GPU
             srow0, snrows = L.split_rows(sny, world)[rank]
             sobst = L.pack_obstacle_bits(channel_mask(NX, sny, rows=(srow0, srow0 + snrows)))
-            slat = make_lattice(sny, srow0, snrows, sobst, None, bits=True)
+            slat = make_lattice(sny, srow0, snrows, sobst, bits=True)
             sms, _ = timed_runs(slat, 2, 1)
             sinfo = slat.info()
             slat.close()
@@ -628,7 +643,7 @@ def main():
 
         def one_e2e_step(obstacles, bits):
             t = [time.perf_counter()]
-            lt = make_lattice(ny, row0, nrows, obstacles, global_free, bits=bits); t.append(time.perf_counter())
+            lt = make_lattice(ny, row0, nrows, obstacles, bits=bits); t.append(time.perf_counter())
             lt.run(T, out=av_host); t.append(time.perf_counter())
             lt.final_fields(out=[o.array for o in out]); t.append(time.perf_counter())
             lt.close(); t.append(time.perf_counter())
