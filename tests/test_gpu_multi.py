@@ -90,6 +90,27 @@ def test_slab_handles_refuse_a_shared_device():
         a.close(); b.close()
 
 
+def test_connect_all_checks_the_descriptor_list():
+    """lbm_gpu_ipc_connect_all refuses lists that do not tile the grid, and slabs that share a GPU."""
+    nx, ny = 64, 16
+    a = L.Lattice(nx, ny, D, A, W, slab=(0, 8), device_ids=[0])
+    b = L.Lattice(nx, ny, D, A, W, slab=(8, 8), device_ids=[0])
+    c = L.Lattice(nx, ny, D, A, W, slab=(4, 8), device_ids=[0])
+    try:
+        with pytest.raises(L.LbmError, match="cover the grid"):
+            a.ipc_connect_all(np.stack([a.ipc_export()]))
+        with pytest.raises(L.LbmError, match="cover the grid"):
+            a.ipc_connect_all(np.stack([a.ipc_export(), b.ipc_export(), c.ipc_export()]))
+        with pytest.raises(L.LbmError, match="next to this slab"):
+            a.ipc_connect_all(np.stack([a.ipc_export(), c.ipc_export()]))       # 16 rows, but nobody holds rows 8..
+        with pytest.raises(L.LbmError, match="same physical GPU|must not share"):
+            a.ipc_connect_all(np.stack([a.ipc_export(), b.ipc_export()]))
+        with pytest.raises(L.LbmError, match="not connected"):
+            a.run(1)
+    finally:
+        a.close(); b.close(); c.close()
+
+
 @pytest.mark.parametrize("mode", ["events", "flags", "default"])
 def test_real_multi_gpu_equals_single(mode):
     n = min(ndev(), 4)
