@@ -83,6 +83,20 @@ def test_default_build_gives_the_bits_of_the_one_step_kernel(nx, ny):
     np.testing.assert_allclose(res[1][1].astype(np.float64), av_ref_d, rtol=1e-5, atol=0)
 
 
+def test_long_run_stays_bit_identical_to_the_one_step_kernel():
+    """3001 timesteps of a channel with obstacles: the two-step kernel (several strips, several
+    segments, an odd last step) and the one-step kernel end in the same bits."""
+    nx, ny, steps = 2052, 300, 3001
+    cells, obst = O.random_lattice(nx, ny, seed=9, p_obst=0.01)
+    res = []
+    for k in (L.KERNEL_VEC4, L.KERNEL_TB2):
+        with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=k) as lat:
+            av = lat.run(steps)
+            res.append((lat.digest(), av))
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1]) and np.all(np.isfinite(res[0][1]))
+
+
 @pytest.mark.parametrize("kernel", TWO_STEP)
 def test_chunked_runs_equal_one_run(kernel):
     """run(a); run(b) == run(a+b) for odd and even pieces: a lone step between two-step passes
