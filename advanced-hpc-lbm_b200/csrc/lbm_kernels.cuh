@@ -326,7 +326,7 @@ template <typename real>
 __device__ __forceinline__ unsigned long long quad_sum_fixed(real s0, real s1, real s2, real s3, bool& bad) {
   typedef Ops<real, true> M;
   const real s = M::add(M::add(s0, s1), M::add(s2, s3));
-  bad = !(s < (real)LBM_SPEED_LIMIT);
+  bad = !(s < (real)(4.0 * LBM_SPEED_LIMIT));     // the bound of four cells
   return to_fixed(s);
 }
 
@@ -1036,7 +1036,7 @@ __device__ __forceinline__ unsigned long long scalar_tile(const StepArgs<real>& 
     t = M::add(t, __shfl_xor_sync(0xffffffffu, t, 2));
     const bool lead = (threadIdx.x & 3) == 0;
     q = lead ? to_fixed(t) : 0ULL;
-    bad = lead && !(t < (real)LBM_SPEED_LIMIT);
+    bad = lead && !(t < (real)(4.0 * LBM_SPEED_LIMIT));
   }
   if (active && bad) atomicOr(a.av + 1, LBM_NONFINITE_MARK);
   return q;
