@@ -467,7 +467,7 @@ class Grid : public GridBase {
   }
 
   // K7 (two timesteps per pass) needs fp32, a width the 16-byte bulk copies can cut (multiple
-  // of 4, at least one 512-column span), slabs tall enough for two-row ghost zones, and no
+  // of 4), slabs tall enough for two-row ghost zones, and no
   // kernel forced by the caller.  Every slab of the grid must come to the same answer: the
   // ghost-row pushes and the flag protocol count passes, not timesteps.
   bool tb2_possible(int rows_min) const {

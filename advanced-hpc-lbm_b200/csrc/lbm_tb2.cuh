@@ -6,12 +6,12 @@
 // (d2q9-bgk.c:180-201, per-cell work :961-1131) while each distribution is read from HBM
 // once and written once: 36 B per update plus halo overhead.
 //
-// Decomposition.  A block owns a "strip" of `wout` <= 504 columns and a "segment" of
+// Decomposition.  A block owns a "strip" of `wout` <= 376 columns and a "segment" of
 // `seg_rows` rows, and marches through the segment row by row (y is the streaming
 // direction, so there is no halo recomputation in y except two rows per segment):
 //
 //   iteration i, row r = R0 - 1 + i:
-//     1. the nine pulled plane-rows of row r (512 columns: the strip plus 4 halo columns on
+//     1. the nine pulled plane-rows of row r (384 columns: the strip plus 4 halo columns on
 //        each side) arrive in shared memory by bulk asynchronous copies (cp.async.bulk,
 //        issued two rows ahead by one thread, completion on an mbarrier) -- rows 0,1,3 from
 //        row r, 2,5,6 from r-1, 4,7,8 from r+1, exactly the reads of K1a, each HBM element
@@ -25,7 +25,7 @@
 //        stores to the destination lattice with 128-bit stores; edge rows are also pushed
 //        into the neighbours' ghost rows, row ny-2 also (accelerated) into the side row.
 //
-//   Sub-step 1 is valid on span columns [1, 511), sub-step 2 on [2, 510); a thread stores
+//   Sub-step 1 is valid on span columns [1, 383), sub-step 2 on [2, 382); a thread stores
 //   only quads inside the owned columns [4, 4 + wout).  Each sub-step's |u| sum counts owned
 //   cells of the segment's own rows only, so av_vels[t] and av_vels[t+1] are exact.
 //
@@ -36,13 +36,16 @@
 
 namespace lbm {
 
-#define LBM_TB2_THREADS 128
+#ifndef LBM_TB2_THREADS
+#define LBM_TB2_THREADS 96          /* one 384-column strip per block: as fast as 128 threads at 16384^2 and up to
+                                       36 % faster on mid-size grids (more, smaller blocks), profiles/r02_kernel_variants.md */
+#endif
 #define LBM_TB2_SPAN (LBM_TB2_THREADS * 4)            /* columns loaded per strip */
 #define LBM_TB2_PAD 4                                  /* floats left and right of a staged row */
-#define LBM_TB2_ROWF (LBM_TB2_SPAN + 2 * LBM_TB2_PAD) /* 520 floats = 2080 B, a multiple of 16 B */
+#define LBM_TB2_ROWF (LBM_TB2_SPAN + 2 * LBM_TB2_PAD) /* 392 floats = 1568 B, a multiple of 16 B */
 #define LBM_TB2_MAX_WOUT (LBM_TB2_SPAN - 8)           /* owned columns per strip */
 #ifndef LBM_TB2_MIN_BLOCKS
-#define LBM_TB2_MIN_BLOCKS 3                           /* 3 x 72.8 KB of shared memory per SM */
+#define LBM_TB2_MIN_BLOCKS 4                           /* 4 x 54.9 KB of shared memory per SM, 12 warps */
 #endif
 
 struct Tb2Smem {
@@ -53,7 +56,7 @@ struct Tb2Smem {
   unsigned long long mbar[2];         // "stage filled" (transaction barriers of the bulk copies)
   unsigned long long mbar_free;       // "ring slots of the previous iteration have been read" (one arrival per warp)
 };
-static_assert(sizeof(Tb2Smem) <= 75 * 1024, "three blocks per SM need <= 75 KB each");
+static_assert(sizeof(Tb2Smem) * LBM_TB2_MIN_BLOCKS <= 225 * 1024, "LBM_TB2_MIN_BLOCKS blocks of shared memory per SM");
 static_assert((LBM_TB2_ROWF * sizeof(float)) % 16 == 0, "staged rows must keep 16-byte alignment");
 
 struct Tb2Args {
@@ -61,7 +64,7 @@ struct Tb2Args {
   const uint32_t* ghost_mask;      // own window: mask words of row -1, then of row `rows`
   unsigned long long* av2;         // sums of sub-step 2
   int wout;                        // owned columns per strip (multiple of 4, <= LBM_TB2_MAX_WOUT)
-  int span;                        // staged columns per strip = threads x 4: 512, or nx + 8 for a narrow grid
+  int span;                        // staged columns per strip = threads x 4 (384), or nx + 8 for a narrow grid
   int seg_rows;                    // rows per segment
 };
 

@@ -16,8 +16,9 @@ VARIANTS = {
     "mb4": ["-DLBM_MIN_BLOCKS=4", "-DLBM_PERSIST_MIN_BLOCKS=3"],
     "scalar": ["-DLBM_PACKED=0"],
     "scalar_mb5": ["-DLBM_PACKED=0", "-DLBM_MIN_BLOCKS=5", "-DLBM_PERSIST_MIN_BLOCKS=4"],
-    "tb2_mb2": ["-DLBM_TB2_MIN_BLOCKS=2"],
-    "tb2_x_nobarrier": ["-DLBM_EXPERIMENTS", "-DLBM_TB2_EXPERIMENT_NO_SECOND_BARRIER"],   # wrong results, timing only
+    "tb2_mb2": ["-DLBM_TB2_THREADS=128", "-DLBM_TB2_MIN_BLOCKS=2"],
+    "tb2_t128": ["-DLBM_TB2_THREADS=128", "-DLBM_TB2_MIN_BLOCKS=3"],
+    "tb2_t64": ["-DLBM_TB2_THREADS=64", "-DLBM_TB2_MIN_BLOCKS=6"],
 }
 if os.environ.get("LBM_VARIANTS"):
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ["LBM_VARIANTS"].split(",")}
