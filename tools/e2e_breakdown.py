@@ -44,8 +44,7 @@ for it in range(5):
         lat = L.Lattice(NX, ny, 0.1, 0.005, 1.85, obstacles=pin.array, slab=(row0, nrows), device_ids=[local],
                         flags=L.POOL)
         t.append(time.perf_counter())
-        below, above = slabs.exchange_descriptors(lat.ipc_export(), rank, world, dist)
-        lat.ipc_connect(below, above)
+        lat.ipc_connect_all(slabs.gather_descriptors(lat.ipc_export(), world, dist))
         t.append(time.perf_counter())
         bar(); lat.ipc_prepare(); bar()
         t.append(time.perf_counter())
