@@ -65,6 +65,10 @@ static_assert(
 #ifndef LBM_STORE_MODE
 #define LBM_STORE_MODE 0            // 0 plain, 1 st.global.cs (streaming), 2 st.global.cg
 #endif
+#ifndef LBM_BARRIER_MODE
+#define LBM_BARRIER_MODE 1          // grid barrier of K5/K9: 1 = red.release + acquire spin; 0 = fence + atomic + spin + fence
+                                    // (4-12 % slower per timestep on L2-resident grids, profiles/r02_kernel_variants.md)
+#endif
 #ifndef LBM_PACKED
 #define LBM_PACKED 1                // default fp32 collision: 1 = packed f32x2 lanes (two cells per instruction),
 #endif                              // 0 = the same operation sequence one cell at a time (same bits)
@@ -1090,13 +1094,21 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, const unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
+#if LBM_BARRIER_MODE == 1
+    // one release-reduction instead of fence + atomic + fence: the release is cumulative over
+    // what the block's threads wrote before the __syncthreads, the acquire loads order what follows
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ULL) : "memory");
+#else
     __threadfence();
     atomicAdd(counter, 1ULL);
+#endif
     unsigned spins = 0;
     while (ld_acquire_gpu(counter) < target) {
       if (++spins == 0x10000000u) __trap();
     }
+#if LBM_BARRIER_MODE != 1
     __threadfence();
+#endif
   }
   __syncthreads();
 }

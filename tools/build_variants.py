@@ -17,6 +17,7 @@ VARIANTS = {
     "scalar": ["-DLBM_PACKED=0"],
     "scalar_mb5": ["-DLBM_PACKED=0", "-DLBM_MIN_BLOCKS=5", "-DLBM_PERSIST_MIN_BLOCKS=4"],
     "tb2_mb2": ["-DLBM_TB2_THREADS=128", "-DLBM_TB2_MIN_BLOCKS=2"],
+    "barrier0": ["-DLBM_BARRIER_MODE=0"],
     "tb2_t128": ["-DLBM_TB2_THREADS=128", "-DLBM_TB2_MIN_BLOCKS=3"],
     "tb2_t64": ["-DLBM_TB2_THREADS=64", "-DLBM_TB2_MIN_BLOCKS=6"],
 }
