@@ -61,7 +61,7 @@ struct CudaError {
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 constexpr int kPersistScalarBlocks = 296;      // measured, profiles/r01_small_grids.md
-constexpr long long kPersistMaxCells = 1536 * 1024;   // K5 while both buffers (72 B per cell) stay well inside the 126 MB L2
+constexpr long long kPersistMaxCells = 1280 * 1024;   // K5 up to here (1024^2: 109 GLUPS against 63 for K7); from 1280^2 on K7 wins (profiles/r02_kernel_variants.md)
 constexpr size_t kStagingBytes = 64u << 20;   // device staging for AoS<->SoA / mask / fields
 
 // descriptor exchanged between processes (lbm_gpu_ipc_export / _connect)
