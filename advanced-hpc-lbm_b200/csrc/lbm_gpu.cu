@@ -170,6 +170,7 @@ class Grid : public GridBase {
   int cur = 0;                 // lattice buffer / window parity holding the current state (flips per pass)
   bool tb2 = false;            // two timesteps per pass (K7) wherever two steps remain
   int tb2_strips = 0, tb2_wout = 0, tb2_seg_rows = 0, tb2_span = 0, tb2_threads = 0;
+  int tb2_tail_rows = 16, tb2_tail_segs = 0;   // K7: height and number of the short segments that end a launch
   int pairs_tile_rows = 0;     // K9: rows per block
   bool failed = false;         // a neighbour never arrived: the lattice contents are void
   unsigned long long timeout_ns = 10000000000ULL;
@@ -513,21 +514,38 @@ class Grid : public GridBase {
         if (score > best + 1e-9) { best = score; tb2_seg_rows = h; }
       }
       if (const char* e = getenv("LBM_TB2_SEG_ROWS")) tb2_seg_rows = std::max(2, atoi(e));   // tuning knob
+      // A block lives (segment height) x ~2.6 us; the last blocks of a launch to be scheduled
+      // leave the other SMs idle for about half of that.  So the launch ENDS with short
+      // segments -- one set of resident blocks' worth, given the highest block indices -- and the
+      // SMs drain together (tall slabs only: the short segments pay 2 halo rows per 16).
+      tb2_tail_segs = (int)((resident + tb2_strips - 1) / tb2_strips) + 1;
+      if (const char* e = getenv("LBM_TB2_TAIL_ROWS")) tb2_tail_rows = atoi(e);                // tuning knob, 0 = off
+      if (tb2_tail_rows < 2) tb2_tail_segs = 0;
       tb2 = true;
       kernel = LBM_GPU_KERNEL_TB2;
     }
   }
 
-  // segments of a slab for K7: equal heights, and the last one keeps at least two rows (the
-  // rows that push into the neighbour above must sit in an edge segment)
-  void tb2_segments(int rows, int& seg_rows, int& nsegs) const {
-    nsegs = std::max(1, (rows + tb2_seg_rows - 1) / tb2_seg_rows);
+  // segments of a slab for K7: n_big segments of equal height, then (tall slabs) n_tail short
+  // ones; the last segment keeps at least two rows (the rows that push into the neighbour
+  // above must sit in an edge segment)
+  struct Tb2Segments { int seg_rows, n_big, big_rows, seg_rows_tail, n_tail; };
+  Tb2Segments tb2_segments(int rows) const {
+    Tb2Segments g;
+    // measured (profiles/r02_kernel_variants.md): +1.2 % on 16384 rows, nothing on 8192, -2 % on 2048
+    const long long min_rows = (long long)tb2_tail_segs * tb2_tail_rows * (tb2_tail_rows >= 8 ? 32 : 4);
+    g.n_tail = (tb2_tail_segs > 0 && min_rows <= rows) ? tb2_tail_segs : 0;
+    g.seg_rows_tail = tb2_tail_rows;
+    g.big_rows = rows - g.n_tail * g.seg_rows_tail;
+    int nsegs = std::max(1, (g.big_rows + tb2_seg_rows - 1) / tb2_seg_rows);
     for (;;) {
-      seg_rows = (rows + nsegs - 1) / nsegs;
-      nsegs = (rows + seg_rows - 1) / seg_rows;
-      if (nsegs == 1 || rows - (nsegs - 1) * seg_rows >= 2) return;
+      g.seg_rows = (g.big_rows + nsegs - 1) / nsegs;
+      nsegs = (g.big_rows + g.seg_rows - 1) / g.seg_rows;
+      if (nsegs == 1 || g.n_tail > 0 || g.big_rows - (nsegs - 1) * g.seg_rows >= 2) break;
       nsegs--;
     }
+    g.n_big = nsegs;
+    return g;
   }
 
   // K9 (two timesteps per grid barrier) for the small grids the persistent kernel K5 would
@@ -881,8 +899,8 @@ class Grid : public GridBase {
       if (two) {
         if constexpr (sizeof(real) == 4) {
           lbm::Tb2Args ta;
-          int seg_rows, nsegs;
-          tb2_segments(s.rows, seg_rows, nsegs);
+          const Tb2Segments sg = tb2_segments(s.rows);
+          const int nsegs = sg.n_big + sg.n_tail;
           a.tiles_x = tb2_strips;
           a.tiles_y = nsegs;
           a.edge_tiles = 1;
@@ -892,7 +910,10 @@ class Grid : public GridBase {
           ta.av2 = a.av + kAvWords;
           ta.wout = tb2_wout;
           ta.span = tb2_span;
-          ta.seg_rows = seg_rows;
+          ta.seg_rows = sg.seg_rows;
+          ta.n_big = sg.n_big;
+          ta.big_rows = sg.big_rows;
+          ta.seg_rows_tail = sg.seg_rows_tail;
           const dim3 grid((unsigned)((long long)tb2_strips * nsegs));
           if (strict) { if (use_flags) launch_tb2<true, true>(s, ta, grid); else launch_tb2<true, false>(s, ta, grid); }
           else        { if (use_flags) launch_tb2<false, true>(s, ta, grid); else launch_tb2<false, false>(s, ta, grid); }

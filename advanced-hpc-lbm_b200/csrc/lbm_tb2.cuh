@@ -65,7 +65,10 @@ struct Tb2Args {
   unsigned long long* av2;         // sums of sub-step 2
   int wout;                        // owned columns per strip (multiple of 4, <= LBM_TB2_MAX_WOUT)
   int span;                        // staged columns per strip = threads x 4 (384), or nx + 8 for a narrow grid
-  int seg_rows;                    // rows per segment
+  int seg_rows;                    // rows per segment ...
+  int n_big;                       // ... of the first n_big segments, which cover rows [0, big_rows);
+  int big_rows;                    // the segments behind them are seg_rows_tail rows tall: they get the highest
+  int seg_rows_tail;               // block indices, so a launch ends with short blocks and the SMs drain together
 };
 
 __device__ __forceinline__ void tb2_mbar_wait(unsigned long long* bar, const uint32_t parity) {
@@ -158,8 +161,9 @@ __device__ __forceinline__ void tb2_tile(const Tb2Args& ta, Tb2Smem& sm, const i
   const int tid = threadIdx.x;
   const int X0 = strip * ta.wout;                              // first owned column
   const int S0 = (X0 >= LBM_TB2_PAD) ? X0 - LBM_TB2_PAD : X0 - LBM_TB2_PAD + a.nx;   // first staged column
-  const int R0 = seg * ta.seg_rows;
-  const int R1 = min(R0 + ta.seg_rows, a.rows);
+  const bool big = seg < ta.n_big;
+  const int R0 = big ? seg * ta.seg_rows : ta.big_rows + (seg - ta.n_big) * ta.seg_rows_tail;
+  const int R1 = big ? min(R0 + ta.seg_rows, ta.big_rows) : min(R0 + ta.seg_rows_tail, a.rows);
   const int n_it = R1 - R0 + 2;                                // sub-step-1 rows R0-1 .. R1
 
   // the quad's column inside the span (threads beyond the span idle along on its last quad)

@@ -63,6 +63,20 @@ def test_every_segment_height(rows_per_segment, seg_rows):
     np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
 
 
+@pytest.mark.parametrize("tail_rows", [2, 3, 0])
+def test_short_segments_at_the_end_of_a_launch(tail_rows, monkeypatch):
+    """Tall slabs end a launch with short segments (so that the SMs drain together): same bits."""
+    monkeypatch.setenv("LBM_TB2_TAIL_ROWS", str(tail_rows))
+    nx, ny, steps = 1024, 1700, 5
+    cells, obst = O.random_lattice(nx, ny, seed=40 + tail_rows, p_obst=0.01)
+    ref, _, av_ref_d = O.run(cells, obst, steps, D, A, W)
+    with L.Lattice(nx, ny, D, A, W, cells=cells, obstacles=obst, flags=L.STRICT | L.KERNEL_TB2) as lat:
+        av = lat.run(steps)
+        _, cs = lat.digest()
+    assert cs == L.lattice_checksum(ref)
+    np.testing.assert_allclose(av.astype(np.float64), av_ref_d, rtol=1e-7, atol=0)
+
+
 @pytest.mark.parametrize("nx,ny", [(512, 16), (1024, 40), (2052, 33), (128, 128)])
 def test_default_build_gives_the_bits_of_the_one_step_kernel(nx, ny):
     steps = 21
