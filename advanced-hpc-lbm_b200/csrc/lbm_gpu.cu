@@ -1495,7 +1495,7 @@ void ipc_connect_impl(Grid<float>& g, const IpcDesc& dn, const IpcDesc& up, bool
   g.use_flags = true;      // neighbours are other processes: device-side flags
   if (g.flags & LBM_GPU_KERNEL_TB2) {
     if (!ring_tb2) throw CudaError{"the two-step kernel needs lbm_gpu_ipc_connect_all and fp32, nx a multiple of 4 "
-                                   "and >= 512, >= 8 rows on every rank"};
+                                   "and >= 32, >= 8 rows on every rank"};
   }
   if (ring_tb2) g.enable_tb2();
   g.connected = true;
